@@ -1,0 +1,71 @@
+/*
+ * pcrcg_b200.h -- C ABI of libpcrcg_b200.so: the B200 (sm_100a) implementation of PCR-CG's
+ * KPConv feature-extraction hot path.  Plain pointers and sizes only.
+ *
+ * Every function returns 0 on success, non-zero on failure; pcrcg_last_error() then returns a
+ * message (thread local).  "_host" entry points take HOST buffers, copy in, compute on the current
+ * CUDA device and copy out: they are what the reference's FFI for this path would bind.  "_dev"
+ * entry points take DEVICE pointers plus a CUDA stream (cudaStream_t passed as void*) and a caller
+ * provided workspace; they never synchronise and never allocate.
+ *
+ * Reference interfaces replaced (paths relative to the PCR-CG tree; "zip!" = cpp_wrappers.zip!cpp_wrappers/):
+ *   pcrcg_subsample_batch_*  : zip!cpp_subsampling/wrapper.cpp:62-333  subsample_batch(points, batches, sampleDl, max_p)
+ *                              -> zip!cpp_subsampling/grid_subsampling/grid_subsampling.cpp:109-211
+ *   pcrcg_radius_*           : cpp_wrappers/cpp_neighbors/wrapper.cpp:58-238  batch_query(queries, supports, q_batches, s_batches, radius)
+ *                              -> cpp_wrappers/cpp_neighbors/neighbors/neighbors.cpp:211-332
+ *   (further entry points are declared below, next to the kernels they expose)
+ */
+#ifndef PCRCG_B200_H
+#define PCRCG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pcrcg_stream_t;   /* cudaStream_t */
+
+const char* pcrcg_last_error(void);
+int pcrcg_version(void);
+void pcrcg_free(void* host_ptr);            /* frees buffers returned by *_host entry points */
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid subsampling.  points [n,3] fp32 (stacked clouds), lens [nb] int32.  Output order and
+ * barycentre bits are those of the reference (libstdc++ unordered_map iteration order, fp32
+ * sequential sums).  max_p <= 0 : keep all.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcrcg_subsample_ws_bytes(int64_t n, int32_t nb);
+/* out_points must hold n*3 floats (upper bound), out_lens nb int32 (device). */
+int pcrcg_subsample_batch_dev(const float* points, int64_t n, const int32_t* lens, int32_t nb, float sampleDl,
+                              int32_t max_p, float* out_points, int32_t* out_lens, void* ws, size_t ws_bytes,
+                              pcrcg_stream_t stream);
+/* Host buffers in, freshly malloc'ed *out_points ([*out_m,3]) out; out_lens [nb] is caller provided. */
+int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* lens, int32_t nb, float sampleDl,
+                               int32_t max_p, float** out_points, int64_t* out_m, int32_t* out_lens);
+
+/* ---------------------------------------------------------------------------------------------
+ * Radius search.  queries [nq,3], supports [ns,3] fp32; q_lens / s_lens [nb] int32.
+ * Rows: neighbours in ascending (d2, index), global support indices, padded with ns.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcrcg_radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
+/* Step 1: bin the supports (grid state is kept inside ws). */
+int pcrcg_radius_build_dev(const float* supports, int64_t ns, const int32_t* s_lens, int32_t nb, float radius,
+                           void* ws, size_t ws_bytes, pcrcg_stream_t stream);
+/* Step 2: query.  rows may be NULL (count only).  rows is [nq,row_stride] int32 of which the first
+ * `width` columns are written; counts [nq] (may be NULL) gets the un-truncated neighbour count;
+ * max_count (device int32, may be NULL) its maximum. */
+int pcrcg_radius_query_dev(const float* queries, int64_t nq, const int32_t* q_lens, int64_t ns, int32_t nb, float radius,
+                           int32_t width, int32_t row_stride, int32_t* rows, int32_t* counts, int32_t* max_count,
+                           void* ws, size_t ws_bytes, pcrcg_stream_t stream);
+/* Host buffers in; *out_rows is malloc'ed [nq,*out_width] with *out_width = max_count when limit<=0
+ * (the reference's output) or min(limit, max_count). */
+int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* supports, int64_t ns, const int32_t* q_lens,
+                           const int32_t* s_lens, int32_t nb, float radius, int32_t limit, int32_t** out_rows,
+                           int32_t* out_width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

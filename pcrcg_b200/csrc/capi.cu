@@ -1,0 +1,131 @@
+// C ABI of libpcrcg_b200.so (see include/pcrcg_b200.h).
+#include "../../include/pcrcg_b200.h"
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace pcrcg {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+size_t subsample_ws_bytes(int64_t n, int32_t nb);
+int subsample_batch_dev(const float*, int64_t, const int32_t*, int32_t, float, int32_t, float*, int32_t*, void*, size_t, cudaStream_t);
+size_t radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
+int radius_build_dev(const float*, int64_t, const int32_t*, int32_t, float, void*, size_t, cudaStream_t);
+int radius_query_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, float, int32_t, int32_t, int32_t*, int32_t*, int32_t*,
+                     void*, size_t, cudaStream_t);
+
+// RAII device buffer for the host entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { PCRCG_CUDA(cudaMalloc(&p, bytes > 0 ? bytes : 1)); return PCRCG_OK; }
+    template <class T> T* as() { return (T*)p; }
+};
+}  // namespace pcrcg
+
+using namespace pcrcg;
+
+extern "C" {
+
+const char* pcrcg_last_error(void) { return g_err; }
+int pcrcg_version(void) { return 100; }
+void pcrcg_free(void* p) { free(p); }
+
+size_t pcrcg_subsample_ws_bytes(int64_t n, int32_t nb) { return subsample_ws_bytes(n, nb); }
+
+int pcrcg_subsample_batch_dev(const float* points, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p,
+                              float* out_points, int32_t* out_lens, void* ws, size_t ws_bytes, pcrcg_stream_t stream)
+{
+    return subsample_batch_dev(points, n, lens, nb, dl, max_p, out_points, out_lens, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p,
+                               float** out_points, int64_t* out_m, int32_t* out_lens)
+{
+    PCRCG_REQUIRE(points && lens && out_points && out_m && out_lens, "subsample_batch: null argument");
+    PCRCG_REQUIRE(n >= 1 && nb >= 1, "Error");   // the reference raises RuntimeError("Error") on an empty result
+    DevBuf dp, dl_, dout, dol, dws;
+    size_t wsb = subsample_ws_bytes(n, nb);
+    PCRCG_TRY(dp.alloc(sizeof(float) * 3 * n));
+    PCRCG_TRY(dl_.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dout.alloc(sizeof(float) * 3 * n));
+    PCRCG_TRY(dol.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dws.alloc(wsb));
+    PCRCG_CUDA(cudaMemcpy(dp.p, points, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    PCRCG_CUDA(cudaMemcpy(dl_.p, lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
+    PCRCG_TRY(subsample_batch_dev(dp.as<float>(), n, dl_.as<int32_t>(), nb, dl, max_p, dout.as<float>(), dol.as<int32_t>(),
+                                  dws.p, wsb, 0));
+    PCRCG_CUDA(cudaMemcpy(out_lens, dol.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost));
+    int64_t m = 0;
+    for (int b = 0; b < nb; b++) m += out_lens[b];
+    PCRCG_REQUIRE(m >= 1, "Error");
+    float* o = (float*)malloc(sizeof(float) * 3 * m);
+    PCRCG_REQUIRE(o != nullptr, "subsample_batch: out of host memory");
+    cudaError_t e = cudaMemcpy(o, dout.p, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(o); set_error("subsample_batch: D2H failed: %s", cudaGetErrorString(e)); return PCRCG_ERR; }
+    *out_points = o;
+    *out_m = m;
+    return PCRCG_OK;
+}
+
+size_t pcrcg_radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb) { return radius_ws_bytes(nq, ns, nb); }
+
+int pcrcg_radius_build_dev(const float* supports, int64_t ns, const int32_t* s_lens, int32_t nb, float radius, void* ws,
+                           size_t ws_bytes, pcrcg_stream_t stream)
+{
+    return radius_build_dev(supports, ns, s_lens, nb, radius, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pcrcg_radius_query_dev(const float* queries, int64_t nq, const int32_t* q_lens, int64_t ns, int32_t nb, float radius,
+                           int32_t width, int32_t row_stride, int32_t* rows, int32_t* counts, int32_t* max_count, void* ws,
+                           size_t ws_bytes, pcrcg_stream_t stream)
+{
+    return radius_query_dev(queries, nq, q_lens, ns, nb, radius, width, row_stride, rows, counts, max_count, ws, ws_bytes,
+                            (cudaStream_t)stream);
+}
+
+int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* supports, int64_t ns, const int32_t* q_lens,
+                           const int32_t* s_lens, int32_t nb, float radius, int32_t limit, int32_t** out_rows,
+                           int32_t* out_width)
+{
+    PCRCG_REQUIRE(queries && supports && q_lens && s_lens && out_rows && out_width, "batch_query: null argument");
+    PCRCG_REQUIRE(nq >= 1 && ns >= 1 && nb >= 1, "Error");
+    DevBuf dq, ds, dql, dsl, dws, dmax, drows;
+    size_t wsb = radius_ws_bytes(nq, ns, nb);
+    PCRCG_TRY(dq.alloc(sizeof(float) * 3 * nq));
+    PCRCG_TRY(ds.alloc(sizeof(float) * 3 * ns));
+    PCRCG_TRY(dql.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dsl.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dws.alloc(wsb));
+    PCRCG_TRY(dmax.alloc(sizeof(int32_t)));
+    PCRCG_CUDA(cudaMemcpy(dq.p, queries, sizeof(float) * 3 * nq, cudaMemcpyHostToDevice));
+    PCRCG_CUDA(cudaMemcpy(ds.p, supports, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice));
+    PCRCG_CUDA(cudaMemcpy(dql.p, q_lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
+    PCRCG_CUDA(cudaMemcpy(dsl.p, s_lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
+    PCRCG_TRY(radius_build_dev(ds.as<float>(), ns, dsl.as<int32_t>(), nb, radius, dws.p, wsb, 0));
+    PCRCG_TRY(radius_query_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, 0, 0, nullptr, nullptr, dmax.as<int32_t>(),
+                               dws.p, wsb, 0));
+    int32_t mx = 0;
+    PCRCG_CUDA(cudaMemcpy(&mx, dmax.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PCRCG_REQUIRE(mx >= 1, "Error");      // cpp_neighbors/wrapper.cpp:201-205
+    int32_t width = (limit > 0 && limit < mx) ? limit : mx;
+    PCRCG_TRY(drows.alloc(sizeof(int32_t) * (size_t)nq * width));
+    PCRCG_TRY(radius_query_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, width, width, drows.as<int32_t>(), nullptr,
+                               nullptr, dws.p, wsb, 0));
+    int32_t* o = (int32_t*)malloc(sizeof(int32_t) * (size_t)nq * width);
+    PCRCG_REQUIRE(o != nullptr, "batch_query: out of host memory");
+    cudaError_t e = cudaMemcpy(o, drows.p, sizeof(int32_t) * (size_t)nq * width, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(o); set_error("batch_query: D2H failed: %s", cudaGetErrorString(e)); return PCRCG_ERR; }
+    *out_rows = o;
+    *out_width = width;
+    return PCRCG_OK;
+}
+
+}  // extern "C"
