@@ -200,7 +200,7 @@ def test_radius_counts_and_symmetry_full_size():
     assert all((y, x) in a for (x, y) in list(a)[:200000])
     # ascending distances inside each row
     d = np.linalg.norm(pts[np.minimum(rows, n - 1)] - pts[:, None, :], axis=2)
-    d[rows >= n] = np.inf
+    d[rows >= n] = 1e9
     assert (np.diff(d, axis=1) >= -1e-7).all()
 
 
