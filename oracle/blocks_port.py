@@ -114,3 +114,31 @@ def encoder(x, batch, blocks, pair_segments=None):
             x = resnetb_block(x, q, s, idx, b["params"], b["strided"], seg_in, seg_out)
         outs.append(x)
     return x, outs
+
+
+# ---------------------------------------------------------------------------------------------
+INDOOR_ARCHITECTURE = ["simple", "resnetb", "resnetb_strided", "resnetb", "resnetb", "resnetb_strided",
+                       "resnetb", "resnetb", "resnetb_strided", "resnetb", "resnetb"]   # configs/models.py:2-13 (encoder part)
+
+
+def encoder_blocks_from_state_dict(sd, architecture=INDOOR_ARCHITECTURE, first_subsampling_dl=0.025, conv_radius=2.5,
+                                   KP_extent=2.0, prefix=""):
+    """Maps a reference ``KPFCNN.encoder_blocks`` state_dict (models/architectures.py:62-100 naming:
+    ``<i>.KPConv.weights``, ``<i>.KPConv.kernel_points``, ``<i>.unary1.mlp.weight`` ...) onto the
+    block descriptors used by :func:`encoder`."""
+    t = lambda k: torch.as_tensor(sd[prefix + k]).float() if (prefix + k) in sd else None
+    blocks, layer, r = [], 0, first_subsampling_dl * conv_radius
+    for i, name in enumerate(architecture):
+        strided = "strided" in name
+        p = dict(kernel_points=t(f"{i}.KPConv.kernel_points"), weights=t(f"{i}.KPConv.weights"),
+                 KP_extent=r * KP_extent / conv_radius)
+        if name.startswith("simple"):
+            blocks.append(dict(kind="simple", strided=strided, layer=layer, params=p))
+        else:
+            p.update(unary1=t(f"{i}.unary1.mlp.weight"), unary2=t(f"{i}.unary2.mlp.weight"),
+                     shortcut=t(f"{i}.unary_shortcut.mlp.weight"))
+            blocks.append(dict(kind="resnetb", strided=strided, layer=layer, params=p))
+        if strided:
+            layer += 1
+            r *= 2
+    return blocks
