@@ -65,6 +65,44 @@ int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* suppor
                            const int32_t* s_lens, int32_t nb, float radius, int32_t limit, int32_t** out_rows,
                            int32_t* out_width);
 
+/* ---------------------------------------------------------------------------------------------
+ * KPConv forward -- models/blocks.py:229-374 KPConv.forward(q_pts, s_pts, neighb_inds, x), rigid
+ * kernel, KP_influence 'linear', aggregation 'sum'.  neighb_inds [nq,H] (row stride idx_stride) is
+ * int32 or int64 (idx_is_i64), shadow index = ns.  kernel_points [K,3], weights [K,cin,cout]
+ * (the reference's Parameter layouts), out [nq,cout].  All device pointers.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcrcg_kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K);
+int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
+                             int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, int32_t cin,
+                             const float* kernel_points, int32_t K, float KP_extent, const float* weights, int32_t cout,
+                             float* out, void* ws, size_t ws_bytes, pcrcg_stream_t stream);
+
+/* Dense contraction C[M,N] = A[M,K] * B (* row_scale[m] if not NULL).  B is [K,N] (b_is_nk = 0) or
+ * [N,K] (b_is_nk = 1, nn.Linear.weight of models/blocks.py:490).  Row-major, leading dims in elements. */
+int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc,
+                   int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
+/* 1: force the fp32 CUDA-core contraction (parity anchor); 0: tcgen05 tensor-core path where shapes allow. */
+void pcrcg_gemm_force_simt(int32_t on);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm over the rows of each segment (= fragment pair) -- models/blocks.py:448,456-463 --
+ * fused with LeakyReLU (:501) and the residual sum of ResnetBottleneckBlock.forward (:678).
+ * seg_starts [nseg+1] int32 device.  mean / rstd [nseg,C].
+ *   out = act( (x-mean)*rstd + shortcut' ),  shortcut' = (sc-sc_mean)*sc_rstd | sc | 0,
+ *   act = LeakyReLU(slope) when slope >= 0, identity when slope < 0;  mean == NULL skips the normalisation.
+ * ------------------------------------------------------------------------------------------- */
+int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps,
+                       float* mean, float* rstd, pcrcg_stream_t stream);
+int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
+                       const float* rstd, const float* sc, const float* sc_mean, const float* sc_rstd, float slope,
+                       float* out, pcrcg_stream_t stream);
+
+/* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
+int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,
+                       int32_t idx_stride, float* out, pcrcg_stream_t stream);
+int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq,
+                           int32_t idx_stride, float* out, pcrcg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

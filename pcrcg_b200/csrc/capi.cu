@@ -21,6 +21,17 @@ int radius_build_dev(const float*, int64_t, const int32_t*, int32_t, float, void
 int radius_query_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, float, int32_t, int32_t, int32_t*, int32_t*, int32_t*,
                      void*, size_t, cudaStream_t);
 
+size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K);
+int kpconv_forward_dev(const float*, int64_t, const float*, int64_t, const void*, int, int32_t, int32_t, const float*, int32_t, const float*,
+                       int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t);
+int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
+void gemm_set_force_simt(int);
+int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
+int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
+                 const float*, float, float*, cudaStream_t);
+int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
+int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
+
 // RAII device buffer for the host entry points
 struct DevBuf {
     void* p = nullptr;
@@ -126,6 +137,49 @@ int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* suppor
     *out_rows = o;
     *out_width = width;
     return PCRCG_OK;
+}
+
+size_t pcrcg_kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K) { return kpconv_ws_bytes(nq, ns, cin, K); }
+
+int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds, int32_t idx_is_i64,
+                             int32_t H, int32_t idx_stride, const float* x, int32_t cin, const float* kernel_points, int32_t K,
+                             float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
+                             pcrcg_stream_t stream)
+{
+    return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc, int32_t M, int32_t N,
+                   int32_t K, const float* row_scale, pcrcg_stream_t stream)
+{
+    return gemm_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
+}
+
+void pcrcg_gemm_force_simt(int32_t on) { gemm_set_force_simt(on); }
+
+int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,
+                       pcrcg_stream_t stream)
+{
+    return colstats_dev(x, n, C, seg_starts, nseg, eps, mean, rstd, (cudaStream_t)stream);
+}
+
+int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
+                       const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, pcrcg_stream_t stream)
+{
+    return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, (cudaStream_t)stream);
+}
+
+int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H, int32_t idx_stride,
+                       float* out, pcrcg_stream_t stream)
+{
+    return max_pool_dev(x, ns, C, inds, idx_is_i64, nq, H, idx_stride, out, (cudaStream_t)stream);
+}
+
+int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t idx_stride,
+                           float* out, pcrcg_stream_t stream)
+{
+    return closest_pool_dev(x, ns, C, inds, idx_is_i64, nq, idx_stride, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,158 @@
+"""Pyramid construction with the reference's function names (``datasets/dataloader.py``), running
+on the GPU through libpcrcg_b200.so.
+
+  batch_grid_subsampling_kpconv  <- datasets/dataloader.py:14-52
+  batch_neighbors_kpconv         <- datasets/dataloader.py:54-69
+  collate_fn_descriptor          <- datasets/dataloader.py:203-400 (the pyramid loop :239-359)
+  calibrate_neighbors            <- datasets/dataloader.py:402-434
+
+Where the call happens differs from the reference on purpose: the reference builds the pyramid in
+forked DataLoader workers on the CPU; CUDA cannot be initialised there, so these run in the main
+process on the device that will also run the encoder (the tensors never leave HBM).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _dev_f32(t, device):
+    if not torch.is_tensor(t):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+    return t.to(device=device, dtype=torch.float32, non_blocking=True)
+
+
+def _dev_i32(t, device):
+    if not torch.is_tensor(t):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int32))
+    return t.to(device=device, dtype=torch.int32, non_blocking=True)
+
+
+def batch_grid_subsampling_kpconv(points, batches_len, features=None, labels=None, sampleDl=0.1, max_p=0, verbose=0,
+                                  random_grid_orient=True):
+    """-> (s_points [M,3] f32, s_len [B] i32), on the device of ``points`` (cuda)."""
+    if features is not None or labels is not None:
+        raise NotImplementedError("pcrcg_b200: features/labels subsampling is outside the KPConv hot path")
+    return ops.subsample_batch(points, batches_len, sampleDl, max_p)
+
+
+def batch_neighbors_kpconv(queries, supports, q_batches, s_batches, radius, max_neighbors):
+    """-> int32 [Nq, min(max_neighbors, max_count)] (max_neighbors <= 0: full width)."""
+    return ops.batch_query(queries, supports, q_batches, s_batches, radius, max_neighbors)
+
+
+@torch.no_grad()
+def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pairs=True, long_indices=False,
+                  return_counts=False):
+    """The pyramid loop of ``collate_fn_descriptor`` (datasets/dataloader.py:239-359).
+
+    points [N0,3], lengths [B] = the stacked clouds of one OR MANY fragment pairs
+    ([src0, tgt0, src1, tgt1, ...]); returns the reference's dict keys ``points, neighbors, pools,
+    upsamples, stack_lengths`` (lists per layer, device tensors; index lists int32 unless
+    ``long_indices``) plus ``pair_segments`` (int32 row starts of each pair, per layer) used to keep
+    InstanceNorm statistics per pair.  Index-list widths follow the reference:
+    min(limit, max_count) (datasets/dataloader.py:66-69)."""
+    device = torch.device(device if device is not None else (points.device if torch.is_tensor(points) and points.is_cuda else "cuda"))
+    pts = _dev_f32(points, device)
+    lens = _dev_i32(lengths, device)
+    arch = config.architecture
+    r_normal = config.first_subsampling_dl * config.conv_radius
+    out = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[])
+    pending, counts_out = [], []            # (list name, layer, rows, limit, max_count tensor)
+    layer, layer_blocks = 0, []
+    for block_i, block in enumerate(arch):
+        if "global" in block or "upsample" in block:
+            break
+        if not ("pool" in block or "strided" in block):
+            layer_blocks.append(block)
+            if block_i < len(arch) - 1 and "upsample" not in arch[block_i + 1]:
+                continue
+        limit = int(neighborhood_limits[layer])
+        grid_fine = None
+        if layer_blocks:
+            grid_fine = ops.RadiusGrid(pts, lens, r_normal)
+            conv_i, cnt, mx = grid_fine.query(pts, lens, limit, want_counts=return_counts)
+            pending.append(("neighbors", layer, conv_i, limit, mx))
+            counts_out.append(cnt)
+        else:
+            conv_i = torch.zeros((0, 1), dtype=torch.int32, device=device)
+        if "pool" in block or "strided" in block:
+            dl = 2 * r_normal / config.conv_radius
+            pool_p, pool_b = ops.subsample_batch(pts, lens, dl)
+            if grid_fine is None:
+                grid_fine = ops.RadiusGrid(pts, lens, r_normal)
+            pool_i, _, mxp = grid_fine.query(pool_p, pool_b, limit, want_counts=False)
+            pending.append(("pools", layer, pool_i, limit, mxp))
+            up_i, _, mxu = ops.RadiusGrid(pool_p, pool_b, 2 * r_normal).query(pts, lens, limit, want_counts=False)
+            pending.append(("upsamples", layer, up_i, limit, mxu))
+        else:
+            pool_i = torch.zeros((0, 1), dtype=torch.int32, device=device)
+            pool_p = torch.zeros((0, 3), dtype=torch.float32, device=device)
+            pool_b = torch.zeros((0,), dtype=torch.int32, device=device)
+            up_i = torch.zeros((0, 1), dtype=torch.int32, device=device)
+        out["points"].append(pts)
+        out["neighbors"].append(conv_i)
+        out["pools"].append(pool_i)
+        out["upsamples"].append(up_i)
+        out["stack_lengths"].append(lens)
+        pts, lens = pool_p, pool_b
+        r_normal *= 2
+        layer += 1
+        layer_blocks = []
+    # one host sync for all widths: width = min(limit, max_count)
+    if pending:
+        mxs = torch.cat([p[4] for p in pending]).cpu().tolist()
+        for (name, l, rows, limit, _), mx in zip(pending, mxs):
+            w = min(limit, int(mx))
+            out[name][l] = rows if w == limit else rows[:, :w]
+    if long_indices:
+        for name in ("neighbors", "pools", "upsamples"):
+            out[name] = [t.long() for t in out[name]]
+    # per-pair row starts at every layer
+    segs = []
+    for l in out["stack_lengths"]:
+        if pairs and l.numel() % 2 == 0 and l.numel() > 0:
+            per_pair = l.view(-1, 2).sum(1)
+        else:
+            per_pair = l.sum().view(1)
+        segs.append(torch.cat([torch.zeros(1, dtype=torch.int32, device=device), per_pair.cumsum(0).to(torch.int32)]))
+    out["pair_segments"] = segs
+    if return_counts:
+        out["neighbor_counts"] = counts_out
+    return out
+
+
+def collate_fn_descriptor(list_data, config, neighborhood_limits, device="cuda"):
+    """datasets/dataloader.py:203-400 for the keys the KPConv path consumes.  ``list_data`` items
+    are dicts with ``src_pcd``, ``tgt_pcd`` ([N,3]) and ``src_feats``, ``tgt_feats`` ([N,C]); unlike the
+    reference any number of pairs may be stacked."""
+    pts, lens, feats = [], [], []
+    for d in list_data:
+        for k in ("src", "tgt"):
+            p = np.asarray(d[f"{k}_pcd"], dtype=np.float32)
+            pts.append(p)
+            lens.append(len(p))
+            feats.append(np.asarray(d[f"{k}_feats"], dtype=np.float32))
+    batch = build_pyramid(np.concatenate(pts), np.array(lens, np.int32), config, neighborhood_limits, device=device)
+    batch["features"] = _dev_f32(np.concatenate(feats), batch["points"][0].device)
+    return batch
+
+
+@torch.no_grad()
+def calibrate_neighbors(pair_iter, config, keep_ratio=0.8, samples_threshold=2000, device="cuda"):
+    """datasets/dataloader.py:402-434: histogram of neighbourhood sizes per layer over the pairs of
+    ``pair_iter`` (items: (src [N,3], tgt [M,3])), limit = number of histogram bins whose cumulated
+    mass stays below keep_ratio."""
+    hist_n = int(np.ceil(4 / 3 * np.pi * (config.deform_radius + 1) ** 3))
+    neighb_hists = np.zeros((config.num_layers, hist_n), dtype=np.int64)
+    for src, tgt in pair_iter:
+        pts = np.concatenate([src, tgt]).astype(np.float32)
+        lens = np.array([len(src), len(tgt)], np.int32)
+        b = build_pyramid(pts, lens, config, [hist_n] * 5, device=device, return_counts=True)
+        counts = [np.minimum(c.cpu().numpy(), hist_n) for c in b["neighbor_counts"]]
+        hists = [np.bincount(c, minlength=hist_n)[:hist_n] for c in counts]
+        neighb_hists += np.vstack(hists)
+        if np.min(np.sum(neighb_hists, axis=1)) > samples_threshold:
+            break
+    cumsum = np.cumsum(neighb_hists.T, axis=0)
+    return np.sum(cumsum < (keep_ratio * cumsum[hist_n - 1, :]), axis=0)

@@ -89,3 +89,139 @@ def batch_query(queries, supports, q_lens, s_lens, radius, limit=0):
     w = int(mx.item())
     rows, _, _ = g.query(queries, q_lens, w, want_counts=False)
     return rows
+
+
+# =================================================================================================
+# KPConv operator library (models/blocks.py)
+# =================================================================================================
+def _idx(t):
+    """index tensors: int32 (native) or int64 (the reference's .long() lists) are both taken as is."""
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t, int(t.dtype == torch.int64), t.shape[1], t.stride(0)
+
+
+def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_extent):
+    """models/blocks.py:229-374 (rigid, linear, sum).  -> [Nq, Cout] float32."""
+    _need_cuda(q_pts, s_pts, neighb_inds, x, kernel_points, weights)
+    q_pts, s_pts, x = _f32c(q_pts), _f32c(s_pts), _f32c(x)
+    kernel_points, weights = _f32c(kernel_points), _f32c(weights)
+    idx, is64, H, stride = _idx(neighb_inds)
+    nq, ns, cin = q_pts.shape[0], s_pts.shape[0], x.shape[1]
+    K, cin_w, cout = weights.shape
+    if cin_w != cin or x.shape[0] != ns or idx.shape[0] != nq or kernel_points.shape[0] != K:
+        raise RuntimeError("kpconv_forward: inconsistent shapes")
+    L = lib()
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
+        ws = _ws(L.pcrcg_kpconv_ws_bytes(nq, ns, cin, K), dev)
+        check(L.pcrcg_kpconv_forward_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
+                                         x.data_ptr(), cin, kernel_points.data_ptr(), K, float(KP_extent), weights.data_ptr(),
+                                         cout, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def linear(x, weight):
+    """nn.Linear(bias=False): x [N,Cin] @ weight[Cout,Cin]^T   (models/blocks.py:490,497)"""
+    _need_cuda(x, weight)
+    x, weight = _f32c(x), _f32c(weight)
+    n, cin = x.shape
+    cout = weight.shape[0]
+    out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_gemm_dev(x.data_ptr(), cin, weight.data_ptr(), cin, 1, out.data_ptr(), cout, n, cout, cin, None, _stream()))
+    return out
+
+
+def matmul(a, b):
+    """a [M,K] @ b [K,N] (test helper for the contraction kernels)."""
+    a, b = _f32c(a), _f32c(b)
+    m, k = a.shape
+    n = b.shape[1]
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().pcrcg_gemm_dev(a.data_ptr(), k, b.data_ptr(), n, 0, out.data_ptr(), n, m, n, k, None, _stream()))
+    return out
+
+
+def _seg_starts(n, segments, device):
+    """segments: None (one group = all rows, the reference) or an int32 device tensor [nseg+1] of row starts."""
+    if segments is None:
+        return torch.tensor([0, n], dtype=torch.int32, device=device)
+    return _i32c(segments)
+
+
+def column_stats(x, segments=None, eps=1e-5):
+    x = _f32c(x)
+    n, c = x.shape
+    seg = _seg_starts(n, segments, x.device)
+    nseg = seg.shape[0] - 1
+    mean = torch.empty((nseg, c), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((nseg, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_colstats_dev(x.data_ptr(), n, c, seg.data_ptr(), nseg, float(eps), mean.data_ptr(), rstd.data_ptr(), _stream()))
+    return mean, rstd, seg
+
+
+def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5):
+    """act(IN(x) + [IN](shortcut)) with act = LeakyReLU(slope) or identity (slope=None).
+    models/blocks.py:456-463 (+ :501, :590, :662, :678)."""
+    _need_cuda(x, shortcut)
+    x = _f32c(x)
+    n, c = x.shape
+    mean, rstd, seg = column_stats(x, segments, eps)
+    scm = scr = None
+    if shortcut is not None:
+        shortcut = _f32c(shortcut)
+        if shortcut_norm:
+            scm, scr, _ = column_stats(shortcut, segments, eps)
+    out = torch.empty_like(x)
+    p = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
+                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), out.data_ptr(), _stream()))
+    return out
+
+
+def add_act(x, shortcut, slope):
+    """LeakyReLU(x + shortcut) without normalisation."""
+    x, shortcut = _f32c(x), _f32c(shortcut)
+    n, c = x.shape
+    seg = _seg_starts(n, None, x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), 1, None, None, shortcut.data_ptr(), None, None,
+                                       float(slope), out.data_ptr(), _stream()))
+    return out
+
+
+def max_pool(x, inds):
+    """models/blocks.py:86-102"""
+    _need_cuda(x, inds)
+    x = _f32c(x)
+    idx, is64, H, stride = _idx(inds)
+    nq = idx.shape[0]
+    out = torch.empty((nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_max_pool_dev(x.data_ptr(), x.shape[0], x.shape[1], idx.data_ptr(), is64, nq, H, stride, out.data_ptr(), _stream()))
+    return out
+
+
+def closest_pool(x, inds):
+    """models/blocks.py:71-83"""
+    _need_cuda(x, inds)
+    x = _f32c(x)
+    idx, is64, H, stride = _idx(inds)
+    nq = idx.shape[0]
+    out = torch.empty((nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_closest_pool_dev(x.data_ptr(), x.shape[0], x.shape[1], idx.data_ptr(), is64, nq, stride, out.data_ptr(), _stream()))
+    return out
+
+
+def force_simt_contraction(on):
+    """True: fp32 CUDA-core contraction (parity anchor); False: tcgen05 tensor cores where shapes allow."""
+    lib().pcrcg_gemm_force_simt(1 if on else 0)

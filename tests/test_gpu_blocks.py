@@ -1,0 +1,139 @@
+"""GPU parity: KPConv / blocks / pooling / encoder through the C ABI vs the reference's golden
+vectors (tests/golden, produced by the reference's own models/blocks.py) and vs the PyTorch-fp32
+restatement (oracle/blocks_port.py) on seeded inputs.
+Tolerance (north_star): features within 1e-3, applied normwise: max|a-b| / max|ref| per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import blocks_port as bp
+from pcrcg_b200 import blocks, ops, synthetic, dataloader
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def _d(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _err(a, ref):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    ref = ref.detach().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def blk():
+    return np.load(os.path.join(G, "blocks_ref.npz"))
+
+
+@pytest.fixture(params=["simt", "tensor"], autouse=True)
+def contraction_path(request):
+    ops.force_simt_contraction(request.param == "simt")
+    yield request.param
+    ops.force_simt_contraction(False)
+
+
+def _geom(blk, idx_dtype=torch.int32):
+    P = [_d(blk[f"points_{l}"]) for l in range(4)]
+    nb = [_d(blk[f"neighbors_{l}"], idx_dtype) for l in range(4)]
+    pools = [_d(blk[f"pools_{l}"], idx_dtype) for l in range(4)]
+    ups = [_d(blk[f"upsamples_{l}"], idx_dtype) for l in range(4)]
+    return P, nb, pools, ups
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+def test_kpconv_vs_reference_golden(blk, idx_dtype):
+    P, nb, pools, _ = _geom(blk, idx_dtype)
+    conv = blocks.KPConv(15, 3, 16, 24, 0.05, 0.0625).to(DEV)
+    conv.weights.data.copy_(_d(blk["kpconv_w"])); conv.set_kernel_points(blk["kpconv_kp"])
+    out = conv(P[0], P[0], nb[0], _d(blk["kpconv_x"]))
+    assert out.shape == blk["kpconv_out"].shape and _err(out, blk["kpconv_out"]) < TOL
+    conv1 = blocks.KPConv(15, 3, 1, 8, 0.05, 0.0625).to(DEV)
+    conv1.weights.data.copy_(_d(blk["kpconv1_w"])); conv1.set_kernel_points(blk["kpconv1_kp"])
+    out = conv1(P[1], P[0], pools[0], torch.ones(P[0].shape[0], 1, device=DEV))
+    assert _err(out, blk["kpconv1_out"]) < TOL
+
+
+def test_blocks_vs_reference_golden(blk):
+    P, nb, pools, ups = _geom(blk)
+    batch = dict(points=P, neighbors=nb, pools=pools, upsamples=ups)
+    cfg = blocks.indoor_config(first_feats_dim=64)
+    x1 = torch.ones(P[0].shape[0], 1, device=DEV)
+    sb = blocks.SimpleBlock("simple", 1, 64, 0.0625, 0, cfg).to(DEV)
+    sb.KPConv.weights.data.copy_(_d(blk["simple_w"])); sb.KPConv.set_kernel_points(blk["simple_kp"])
+    xs = sb(x1, batch)
+    assert _err(xs, blk["simple_out"]) < TOL
+    rb = blocks.ResnetBottleneckBlock("resnetb", 32, 64, 0.0625, 0, cfg).to(DEV)
+    rb.load_state_dict({k[3:]: torch.from_numpy(blk[k]) for k in blk.files if k.startswith("rb_") and k != "rb_out"})
+    xr = rb(_d(blk["simple_out"]), batch)
+    assert _err(xr, blk["rb_out"]) < TOL
+    rs = blocks.ResnetBottleneckBlock("resnetb_strided", 64, 64, 0.0625, 0, cfg).to(DEV)
+    rs.load_state_dict({k[3:]: torch.from_numpy(blk[k]) for k in blk.files if k.startswith("rs_") and k != "rs_out"})
+    xo = rs(_d(blk["rb_out"]), batch)
+    assert _err(xo, blk["rs_out"]) < TOL
+
+
+def test_pools_vs_reference_golden_exact(blk):
+    _, _, pools, ups = _geom(blk)
+    assert np.array_equal(blocks.max_pool(_d(blk["pool_x"]), pools[0]).cpu().numpy(), blk["max_pool_out"])
+    assert np.array_equal(blocks.closest_pool(_d(blk["closest_x"]), ups[0]).cpu().numpy(), blk["closest_pool_out"])
+    assert np.array_equal(blocks.max_pool(_d(blk["pool_x"]), pools[0].long()).cpu().numpy(), blk["max_pool_out"])
+
+
+def test_encoder_vs_reference_golden(blk):
+    enc = np.load(os.path.join(G, "encoder_ref.npz"))
+    sd = {k[3:]: enc[k] for k in enc.files if k.startswith("sd_")}
+    net = blocks.KPEncoder(blocks.indoor_config(first_feats_dim=32)).to(DEV)
+    net.load_reference(sd, prefix="")
+    P, nb, pools, ups = _geom(blk)
+    batch = dict(points=P, neighbors=nb, pools=pools, upsamples=ups)
+    x = net(torch.ones(P[0].shape[0], 1, device=DEV), batch)
+    assert x.shape == enc["encoder_out"].shape
+    assert _err(x, enc["encoder_out"]) < TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (129, 128), (256, 256), (512, 512)])
+def test_kpconv_vs_port_channel_sweep(cin, cout):
+    src, tgt, _ = synthetic.match3d_pair(4, n_target=1200)
+    pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+    rows = ops.batch_query(_d(pts), _d(pts), _d(lens), _d(lens), 0.0625, 34)
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(len(pts), cin, generator=g)
+    w = torch.randn(15, cin, cout, generator=g) / np.sqrt(15 * cin)
+    kp = torch.randn(15, 3, generator=g) * 0.03
+    ref = bp.kpconv(torch.from_numpy(pts), torch.from_numpy(pts), rows.cpu(), x, kp, w, 0.05)
+    out = ops.kpconv_forward(_d(pts), _d(pts), rows, x.to(DEV), kp.to(DEV), w.to(DEV), 0.05)
+    assert _err(out, ref) < TOL
+
+
+def test_multi_pair_batch_equals_single_pairs():
+    """Stacking pairs must not change any pair's result: index lists are per cloud and the
+    InstanceNorm statistics are per pair (pair_segments)."""
+    cfg = blocks.indoor_config(first_feats_dim=32)
+    limits = [30, 28, 28, 30]
+    torch.manual_seed(0)
+    net = blocks.KPEncoder(cfg).to(DEV)
+    for m in net.modules():
+        if isinstance(m, blocks.KPConv):
+            m.set_kernel_points(torch.randn(15, 3) * 0.4 * m.radius)
+    pairs = [synthetic.match3d_pair(s, n_target=900 + 150 * s)[:2] for s in range(3)]
+    singles = []
+    for src, tgt in pairs:
+        b = dataloader.build_pyramid(np.concatenate([src, tgt]), np.array([len(src), len(tgt)], np.int32), cfg, limits, device=DEV)
+        singles.append(net(torch.ones(len(src) + len(tgt), 1, device=DEV), b).cpu().numpy())
+    pts = np.concatenate([np.concatenate(p) for p in pairs])
+    lens = np.array([len(c) for p in pairs for c in p], np.int32)
+    b = dataloader.build_pyramid(pts, lens, cfg, limits, device=DEV)
+    y = net(torch.ones(len(pts), 1, device=DEV), b).cpu().numpy()
+    seg = b["pair_segments"][-1].cpu().numpy()
+    for k, s in enumerate(singles):
+        part = y[seg[k]:seg[k + 1]]
+        assert part.shape == s.shape
+        assert np.abs(part - s).max() <= 2e-5 * np.abs(s).max()
