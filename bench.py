@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its named workload.
+
+  metric   : 3DMatch pairs/s for the chain  subsample x3 + radius search x10 + 11 KPConv encoder blocks
+  workload : configs[1] -- a batch of 3DMatch-shaped synthetic fragment pairs (~20k points per
+             fragment, neighbourhood limits frozen with the reference's calibration rule) per GPU
+  step     : one pass of the hot path over one batch of P pairs
+  value    : pairs/s, whole job, inputs resident in HBM when the timed region starts
+  e2e      : the same through the user-facing call with HOST buffers (pinned H2D of the points,
+             D2H of the encoder features) inside the timed region
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload 3dmatch|3dlomatch|kitti]
+Multi GPU: launched by torchrun, one rank per GPU, pairs sharded by rank, no collective on the path
+(NCCL only for the barrier and the max-over-ranks of the timings).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "3DMatch pairs/s (subsample+radius search+KPConv fwd)"
+UNIT = "pairs/s"
+
+
+# ------------------------------------------------------------------------------------------------
+def make_pairs(workload, n_pairs, seed0):
+    from pcrcg_b200 import synthetic
+    pairs = []
+    for i in range(n_pairs):
+        if workload == "3dmatch":
+            s, t, _ = synthetic.match3d_pair(seed0 + i)
+        elif workload == "3dlomatch":
+            s, t, _ = synthetic.match3d_pair(seed0 + i, overlap="low")
+        elif workload == "kitti":
+            a, b, _ = synthetic.kitti_pair(seed0 + i)
+            s, t = synthetic.voxel_downsample_np(a.astype(np.float64), 0.3), synthetic.voxel_downsample_np(b.astype(np.float64), 0.3)
+            s, t = s.astype(np.float32), t.astype(np.float32)
+        else:
+            raise SystemExit(f"unknown workload {workload}")
+        pairs.append((s, t))
+    return pairs
+
+
+def workload_config(workload):
+    from pcrcg_b200 import blocks, pipeline
+    if workload == "kitti":
+        return blocks.kitti_config(), pipeline.CALIBRATED_LIMITS["kitti_synthetic"]
+    key = "3dmatch_synthetic" if workload == "3dmatch" else "3dlomatch_synthetic"
+    return blocks.indoor_config(), pipeline.CALIBRATED_LIMITS[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference path (oracle): the reference's C++ ops + PyTorch-CPU encoder, same weights
+def _cpu_preprocess(args):
+    """One pair's pyramid on one core (the reference runs this inside a DataLoader worker)."""
+    src, tgt, limits, dl0, conv_radius = args
+    import oracle
+    use_ref = oracle.have_ref()
+    R = oracle.ref() if use_ref else oracle.port()
+    pts = np.concatenate([src, tgt]).astype(np.float32)
+    lens = np.array([len(src), len(tgt)], np.int32)
+    out = dict(points=[], neighbors=[], pools=[], upsamples=[])
+    r = dl0 * conv_radius
+
+    def q(qp, sp, ql, sl, rad, lim):
+        rows = R.batch_query(qp, sp, ql, sl, rad)
+        return np.ascontiguousarray(rows[:, :lim])
+    for l in range(4):
+        conv = q(pts, pts, lens, lens, r, limits[l])
+        if l < 3:
+            pp, pl = R.subsample_batch(pts, lens, 2 * r / conv_radius)
+            pool = q(pp, pts, pl, lens, r, limits[l])
+            up = q(pts, pp, lens, pl, 2 * r, limits[l])
+        else:
+            pp, pl, pool, up = pts[:0], lens[:0], np.zeros((0, 1), np.int32), np.zeros((0, 1), np.int32)
+        out["points"].append(pts); out["neighbors"].append(conv); out["pools"].append(pool); out["upsamples"].append(up)
+        pts, lens = pp, pl
+        r *= 2
+    return out
+
+
+def cpu_reference_run(pairs, cfg, limits, state_dict, threads):
+    """Times the CPU path on `pairs`: preprocessing in worker processes (one pair per core, like the
+    reference's DataLoader workers), then the encoder with `threads` torch threads.  -> (pairs/s, kind)"""
+    import concurrent.futures as cf
+    import torch
+    import oracle
+    from oracle import blocks_port as bp
+    kind = "reference" if oracle.have_ref() else "port"
+    torch.set_num_threads(threads)
+    blocks_desc = bp.encoder_blocks_from_state_dict({k: v.cpu() for k, v in state_dict.items()}, prefix="encoder_blocks.",
+                                                    first_subsampling_dl=cfg.first_subsampling_dl, conv_radius=cfg.conv_radius,
+                                                    KP_extent=cfg.KP_extent)
+    jobs = [(s, t, list(limits), cfg.first_subsampling_dl, cfg.conv_radius) for s, t in pairs]
+    t0 = time.perf_counter()
+    workers = max(1, min(threads, len(jobs)))
+    if workers > 1:
+        with cf.ProcessPoolExecutor(workers) as ex:
+            pyrs = list(ex.map(_cpu_preprocess, jobs))
+    else:
+        pyrs = [_cpu_preprocess(j) for j in jobs]
+    t_pre = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for p in pyrs:
+            batch = {k: [torch.from_numpy(np.ascontiguousarray(a)) for a in v] for k, v in p.items()}
+            x = torch.ones(batch["points"][0].shape[0], cfg.in_feats_dim)
+            bp.encoder(x, batch, blocks_desc)
+    t_enc = time.perf_counter() - t0
+    return len(pairs) / (t_pre + t_enc), kind, dict(preprocess_s=round(t_pre, 3), encoder_s=round(t_enc, 3), workers=workers)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t_begin <= ts <= t_end + 0.2:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_work(batch, cfg, limits, enc):
+    """Per-step algorithmic bytes / flops per kernel class (SURVEY.md section 8d formulas)."""
+    from pcrcg_b200 import blocks
+    N = [int(p.shape[0]) for p in batch["points"]]
+    B = int(batch["stack_lengths"][0].numel())
+    W = {k: [int(t.shape[1]) if t.numel() else 0 for t in batch[k]] for k in ("neighbors", "pools", "upsamples")}
+    work = {}
+    sub = sum(12 * N[l] + 4 * B + 12 * N[l + 1] + 4 * B for l in range(len(N) - 1))
+    work["subsample"] = dict(bytes=sub, flops=0)
+    rad = 0
+    for l in range(len(N)):
+        rad += 12 * N[l] + 12 * N[l] + 8 * B + 4 * N[l] * W["neighbors"][l]
+        if l + 1 < len(N):
+            rad += 12 * N[l + 1] + 12 * N[l] + 8 * B + 4 * N[l + 1] * W["pools"][l]
+            rad += 12 * N[l] + 12 * N[l + 1] + 8 * B + 4 * N[l] * W["upsamples"][l]
+    work["radius"] = dict(bytes=rad, flops=0)
+    agg_b = agg_f = gemm_f = gemm_b = lin_f = lin_b = 0
+    K = cfg.num_kernel_points
+    for m in enc.encoder_blocks:
+        l = m.layer_ind
+        strided = "strided" in m.block_name
+        nq, ns = (N[l + 1], N[l]) if strided else (N[l], N[l])
+        H = W["pools"][l] if strided else W["neighbors"][l]
+        conv = m.KPConv
+        cin, cout = conv.in_channels, conv.out_channels
+        agg_b += 4 * nq * H + 4 * ns * cin + 12 * (nq + ns)
+        agg_f += 2 * nq * K * H * cin + 12 * nq * H * K
+        gemm_f += 2 * nq * K * cin * cout
+        gemm_b += 4 * K * cin * cout + 4 * nq * cout
+        if isinstance(m, blocks.ResnetBottleneckBlock):
+            for u, rows in ((m.unary1, ns), (m.unary2, nq), (m.unary_shortcut, nq)):
+                if isinstance(u, blocks.UnaryBlock):
+                    lin_f += 2 * rows * u.in_dim * u.out_dim
+                    lin_b += 4 * (rows * u.in_dim + u.in_dim * u.out_dim + rows * u.out_dim)
+    work["kpconv_aggregate"] = dict(bytes=agg_b, flops=agg_f)
+    work["gemm"] = dict(bytes=gemm_b + lin_b, flops=gemm_f + lin_f, kpconv_flops=gemm_f, linear_flops=lin_f)
+    return work, N
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="3dmatch", choices=["3dmatch", "3dlomatch", "kitti"])
+    ap.add_argument("--pairs", type=int, default=16, help="fragment pairs per step per GPU")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core contraction")
+    args = ap.parse_args()
+    W = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    K = max(args.steps, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+
+    import torch
+    from pcrcg_b200 import blocks, pipeline
+    cfg, limits = workload_config(args.workload)
+    wl_name = {"3dmatch": "configs[1]: 3DMatch-shaped synthetic pair batch (~20k pts/fragment, calibrated limits)",
+               "3dlomatch": "configs[2]: 3DLoMatch-shaped synthetic low-overlap pairs",
+               "kitti": "configs[3]: KITTI-shaped synthetic scans (voxel 0.3, 4-layer KPConv)"}[args.workload]
+
+    # random-init weights of the named architecture, identical on every rank and for both arms
+    torch.manual_seed(0)
+    enc_cpu = blocks.KPEncoder(cfg)
+    pipeline.init_kernel_points(enc_cpu, 0)
+    state_dict = {k: v.clone() for k, v in enc_cpu.state_dict().items()}
+
+    # ---------------------------------------------------------------- reference arm (CPU) ------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = make_pairs(args.workload, 1, 10_000)
+        for _ in range(W):
+            cpu_reference_run(sample, cfg, limits, state_dict, threads)
+        t0 = time.perf_counter()
+        detail = None
+        for k in range(K):
+            _, kind, detail = cpu_reference_run(make_pairs(args.workload, 1, 10_000 + k), cfg, limits, state_dict, threads)
+        dt = time.perf_counter() - t0
+        v = K / dt
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": 1000 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": wl_name, "sample": "1 pair per step", "limits": list(limits),
+                                                "first_feats_dim": cfg.first_feats_dim},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                 "sample": f"{K} steps x 1 synthetic pair: reference C++ subsample/search (1 core) + PyTorch-CPU encoder ({threads} threads)",
+                                 "detail": detail},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- our arm -------------------
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised in this process (the preprocessing workers are forked)
+        sample = make_pairs(args.workload, args.cpu_sample_pairs, 20_000)
+        v, kind, detail = cpu_reference_run(sample, cfg, limits, state_dict, threads)
+        cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                    "sample": f"{len(sample)} synthetic pairs of the same workload: reference C++ subsample/search in {detail['workers']} worker "
+                              f"processes + PyTorch-CPU encoder on {threads} threads", "detail": detail}
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from pcrcg_b200 import ops
+    from pcrcg_b200._lib import lib
+    import ctypes as C
+    L = lib()
+    if args.simt:
+        ops.force_simt_contraction(True)
+
+    P = args.pairs
+    pairs = make_pairs(args.workload, P, rank * P)                  # pair index sharded by rank
+    pts_np, lens_np = pipeline.stack_pairs(pairs)
+    pts_host = torch.from_numpy(pts_np).pin_memory()
+    lens_host = torch.from_numpy(lens_np).pin_memory()
+    path = pipeline.FeaturePath(cfg, limits, device=dev, state_dict=state_dict)
+    pts_dev, lens_dev = pts_host.to(dev), lens_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    y = None
+    for _ in range(W):
+        y, batch = path.run_device(pts_dev, lens_dev)
+    out_host = torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        path.run_host(pts_host, lens_host, out_host)
+    work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder)
+
+    # ---- device-resident timed region ----------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    L.pcrcg_profile_enable(1)
+    launches0 = L.pcrcg_launch_count()
+    barrier()
+    t_begin = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        flush.fill_(0.0)                                  # L2 flush between timed iterations
+        y, _ = path.run_device(pts_dev, lens_dev)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(L.pcrcg_launch_count() - launches0)
+    ncls = L.pcrcg_profile_classes()
+    ms_arr, cnt_arr = (C.c_double * ncls)(), (C.c_int64 * ncls)()
+    L.pcrcg_profile_report(ms_arr, cnt_arr)
+    L.pcrcg_profile_enable(0)
+    prof = {L.pcrcg_profile_class_name(c).decode(): (ms_arr[c], cnt_arr[c]) for c in range(ncls)}
+
+    # ---- end-to-end timed region (host buffers through the public API) ----------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        flush.fill_(0.0)
+        out, _ = path.run_host(pts_host, lens_host, out_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end)
+
+    t = torch.tensor([ms_total, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = t.tolist()
+    value = world * P * K / (ms_total / 1000.0)
+    e2e_value = world * P * K / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        kernels = {}
+        agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
+               "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"]}
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, parts in agg.items():
+            ms = sum(prof[p][0] for p in parts if p in prof) / K
+            n = sum(prof[p][1] for p in parts if p in prof) // K
+            ent = {"ms_per_step": round(ms, 4), "scopes_per_step": int(n), "share": round(ms * K / tot_ms, 4)}
+            if name in work and ms > 0:
+                ent["GB/s"] = round(work[name]["bytes"] / ms / 1e6, 2)
+                if work[name]["flops"]:
+                    ent["TFLOP/s"] = round(work[name]["flops"] / ms / 1e9, 3)
+            kernels[name] = ent
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path):
+            traffic = json.load(open(tr_path)).get(dom)
+        if dom == "gemm":
+            ach = kernels[dom].get("TFLOP/s", 0.0)
+            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": traffic, "peak_source": peak_src + ", bf16 dense sustained"}
+        else:
+            ach = kernels[dom].get("GB/s", 0.0)
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.simt else "f32 (contraction: see config.contraction)", "data": "synthetic",
+                "config": {"workload": wl_name, "pairs_per_step_per_gpu": P, "points_per_level": Nlev, "limits": list(limits),
+                           "first_feats_dim": cfg.first_feats_dim, "l2": "256 MiB flush write between timed iterations",
+                           "contraction": "fp32 CUDA cores" if args.simt else "tcgen05 where shapes allow, else fp32 CUDA cores",
+                           "parallelism": f"pairs sharded by rank x{world}, no collective on the path"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes + lens_np.nbytes),
+                        "d2h_bytes_per_step": int(out.numel() * 4 + lens_np.nbytes), "ms_per_step": e2e_ms / K},
+                "gpu_launches": launches, "roofline": roof, "kernels": kernels}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,15 @@ const char* pcrcg_last_error(void);
 int pcrcg_version(void);
 void pcrcg_free(void* host_ptr);            /* frees buffers returned by *_host entry points */
 
+/* Measurement hooks: per kernel-class device time from CUDA events recorded on the launching stream
+ * around each class's launches (enable, run, report: ms[c] / counts[c] for c < pcrcg_profile_classes()),
+ * and the running count of kernels this library launched. */
+void pcrcg_profile_enable(int32_t on);
+int32_t pcrcg_profile_classes(void);
+const char* pcrcg_profile_class_name(int32_t c);
+int pcrcg_profile_report(double* ms, int64_t* counts);
+uint64_t pcrcg_launch_count(void);
+
 /* ---------------------------------------------------------------------------------------------
  * Grid subsampling.  points [n,3] fp32 (stacked clouds), lens [nb] int32.  Output order and
  * barycentre bits are those of the reference (libstdc++ unordered_map iteration order, fp32

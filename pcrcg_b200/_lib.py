@@ -22,6 +22,11 @@ SIGNATURES = {
     "pcrcg_last_error": (C.c_char_p, []),
     "pcrcg_version": (C.c_int, []),
     "pcrcg_free": (None, [_P]),
+    "pcrcg_profile_enable": (None, [_I32]),
+    "pcrcg_profile_classes": (_I32, []),
+    "pcrcg_profile_class_name": (C.c_char_p, [_I32]),
+    "pcrcg_profile_report": (C.c_int, [_P, _P]),
+    "pcrcg_launch_count": (C.c_uint64, []),
     "pcrcg_subsample_ws_bytes": (_SZ, [_I64, _I32]),
     "pcrcg_subsample_batch_dev": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
     "pcrcg_subsample_batch_host": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, C.POINTER(_P), C.POINTER(_I64), _P]),

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 
 namespace pcrcg {
 static thread_local char g_err[1024] = "";
@@ -13,6 +15,35 @@ void set_error(const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+// ---- profiling ---------------------------------------------------------------------------------
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static int g_prof_on = 0;
+static unsigned long long g_launches = 0;
+static std::mutex g_prof_mu;
+void count_launches(int n) { g_launches += (unsigned long long)n; }
+static cudaEvent_t get_event()
+{
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int cls, cudaStream_t st, int* slot)
+{
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{ cls, get_event(), get_event() };
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    *slot = (int)g_prof.size() - 1;
+}
+void prof_end(int slot, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
 }
 size_t subsample_ws_bytes(int64_t n, int32_t nb);
 int subsample_batch_dev(const float*, int64_t, const int32_t*, int32_t, float, int32_t, float*, int32_t*, void*, size_t, cudaStream_t);
@@ -48,6 +79,30 @@ extern "C" {
 const char* pcrcg_last_error(void) { return g_err; }
 int pcrcg_version(void) { return 100; }
 void pcrcg_free(void* p) { free(p); }
+
+void pcrcg_profile_enable(int32_t on) { g_prof_on = on; }
+uint64_t pcrcg_launch_count(void) { return g_launches; }
+int32_t pcrcg_profile_classes(void) { return PC_COUNT; }
+const char* pcrcg_profile_class_name(int32_t c)
+{
+    static const char* names[PC_COUNT] = { "subsample", "radius_build", "radius_query", "kpconv_aggregate", "gemm", "norm_act", "pool", "projection" };
+    return (c >= 0 && c < PC_COUNT) ? names[c] : "?";
+}
+// Synchronises the device, sums elapsed ms and scope counts per class, clears the records.
+int pcrcg_profile_report(double* ms, int64_t* counts)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int c = 0; c < PC_COUNT; c++) { ms[c] = 0.0; counts[c] = 0; }
+    PCRCG_CUDA(cudaDeviceSynchronize());
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; counts[r.cls] += 1; }
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    return PCRCG_OK;
+}
 
 size_t pcrcg_subsample_ws_bytes(int64_t n, int32_t nb) { return subsample_ws_bytes(n, nb); }
 

@@ -41,6 +41,19 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- per-kernel-class device timing (CUDA events on the launching stream) + launch counter ------
+// Enabled by pcrcg_profile_enable(1); a ProfScope records an event pair around the launches of one
+// kernel class; pcrcg_profile_report() synchronises and sums elapsed times per class.
+enum ProfClass { PC_SUBSAMPLE = 0, PC_RADIUS_BUILD, PC_RADIUS_QUERY, PC_KPCONV_AGG, PC_GEMM, PC_NORM, PC_POOL, PC_PROJECT, PC_COUNT };
+void prof_begin(int cls, cudaStream_t st, int* slot);
+void prof_end(int slot, cudaStream_t st);
+void count_launches(int n);
+struct ProfScope {
+    int slot; cudaStream_t st;
+    ProfScope(int cls, cudaStream_t s, int launches) : slot(-1), st(s) { count_launches(launches); prof_begin(cls, s, &slot); }
+    ~ProfScope() { if (slot >= 0) prof_end(slot, st); }
+};
+
 // ---- caller-provided workspace, bump allocated ------------------------------------------------
 struct Workspace {
     char* base;

@@ -115,6 +115,7 @@ int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
 {
     (void)n;
     PCRCG_REQUIRE(C >= 1 && nseg >= 1 && nseg < 65536, "instance norm: bad dimensions");
+    ProfScope prof(PC_NORM, st, 1);
     k_colstats<<<dim3((unsigned)cdiv64(C, 32), (unsigned)nseg), 256, 0, st>>>(x, C, C, seg_starts, eps, mean, rstd);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
@@ -124,6 +125,7 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
                  const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, cudaStream_t st)
 {
     if (n == 0) return PCRCG_OK;
+    ProfScope prof(PC_NORM, st, 1);
     long long tot = (long long)n * ((C + 3) / 4);
     k_norm_act<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, mean, rstd, sc, C, sc_mean, sc_rstd, slope,
                                                           out, C);
@@ -135,6 +137,7 @@ int max_pool_dev(const float* x, int64_t ns, int32_t C, const void* idx, int idx
                  float* out, cudaStream_t st)
 {
     if (nq == 0) return PCRCG_OK;
+    ProfScope prof(PC_POOL, st, 1);
     unsigned g = (unsigned)cdiv64(nq, 8);
     if (idx_is_i64) k_max_pool<long long><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const long long*)idx, (int)nq, H, idx_stride, out);
     else k_max_pool<int><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const int*)idx, (int)nq, H, idx_stride, out);
@@ -146,6 +149,7 @@ int closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* idx, int
                      cudaStream_t st)
 {
     if (nq == 0) return PCRCG_OK;
+    ProfScope prof(PC_POOL, st, 1);
     unsigned g = (unsigned)cdiv64(nq, 8);
     if (idx_is_i64) k_closest_pool<long long><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const long long*)idx, (int)nq, idx_stride, out);
     else k_closest_pool<int><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const int*)idx, (int)nq, idx_stride, out);

@@ -91,6 +91,7 @@ int gemm_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, floa
 {
     if (M <= 0 || N <= 0) return PCRCG_OK;
     PCRCG_REQUIRE(K >= 1, "gemm: K must be >= 1");
+    ProfScope prof(PC_GEMM, st, 1);
     if (!g_force_simt) {
         bool handled = false;
         PCRCG_TRY(gemm_tc_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, st, &handled));

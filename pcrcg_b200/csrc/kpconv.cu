@@ -156,16 +156,20 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     float* inv_cnt = W.take<float>((size_t)nq);
     uint8_t* rowflag = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
+    ProfScope* prof = new ProfScope(PC_KPCONV_AGG, st, 2);
     if (ns > 0) {
         k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag);
         PCRCG_CUDA(cudaGetLastError());
     }
     const float inv_extent = 1.0f / kp_extent;
     if (idx_is_i64) {
-        PCRCG_TRY(launch_agg<long long>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st));
+        int rc = launch_agg<long long>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st);
+        if (rc) { delete prof; return rc; }
     } else {
-        PCRCG_TRY(launch_agg<int>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st));
+        int rc = launch_agg<int>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st);
+        if (rc) { delete prof; return rc; }
     }
+    delete prof;
     return gemm_dev(wf, K * cin, weights, cout, 0, out, cout, (int)nq, cout, K * cin, inv_cnt, st);
 }
 

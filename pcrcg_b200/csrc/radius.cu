@@ -299,6 +299,9 @@ int radius_build_dev(const float* s, int64_t ns, const int32_t* s_lens, int32_t 
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "radius search: workspace too small (%zu < %zu)", ws_bytes, W.off);
     const int NS = (int)ns;
     const unsigned gs = (unsigned)cdiv64(NS > 0 ? NS : 1, 256);
+    int nbits = 1;
+    while ((1ull << nbits) < 2ull * (uint64_t)NS + (uint64_t)nb + 1ull) nbits++;
+    ProfScope prof(PC_RADIUS_BUILD, st, 8 + 5 * ((nbits + 7) / 8));
     PCRCG_TRY(cloud_starts(s_lens, nb, r.sstarts, st));
     k_rbbox_init<<<(nb * 6 + 255) / 256, 256, 0, st>>>(r.bbox, nb);
     k_rbbox<<<gs, 256, 0, st>>>(s, NS, r.sstarts, nb, r.bbox);
@@ -307,8 +310,6 @@ int radius_build_dev(const float* s, int64_t ns, const int32_t* s_lens, int32_t 
     PCRCG_CUDA(cudaMemsetAsync(r.rep, 0xff, sizeof(uint32_t) * (2 * (size_t)NS + nb), st));
     k_cell_insert<<<gs, 256, 0, st>>>(r.keys, NS, r.sstarts, nb, r.rep, r.slot, r.iota);
     PCRCG_CUDA(cudaGetLastError());
-    int nbits = 1;
-    while ((1ull << nbits) < 2ull * (uint64_t)NS + (uint64_t)nb + 1ull) nbits++;
     PCRCG_TRY(radix_sort_pairs(r.slot, r.iota, r.sslot, r.sidx, NS, nbits, r.prim, r.prim_bytes, st));
     k_cell_runs<<<gs, 256, 0, st>>>(s, r.sslot, r.sidx, NS, r.rec, r.range);
     PCRCG_CUDA(cudaGetLastError());
@@ -326,6 +327,7 @@ int radius_query_dev(const float* q, int64_t nq, const int32_t* q_lens, int64_t 
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "radius search: workspace too small");
     PCRCG_REQUIRE(rows == nullptr || (width >= 0 && row_stride >= width), "radius search: bad row geometry");
     if (nq == 0) return PCRCG_OK;
+    ProfScope prof(PC_RADIUS_QUERY, st, 3);
     PCRCG_TRY(cloud_starts(q_lens, nb, r.qstarts, st));
     if (maxcount) PCRCG_CUDA(cudaMemsetAsync(maxcount, 0, sizeof(int32_t), st));
     const float r2 = radius * radius;      // neighbors.cpp:226 (fp32 product)

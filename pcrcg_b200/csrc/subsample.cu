@@ -314,6 +314,9 @@ int subsample_batch_dev(const float* pts, int64_t n, const int32_t* lens, int32_
     const int N = (int)n;
     const unsigned gb = (unsigned)cdiv64(N > 0 ? N : 1, 256);
 
+    int nbits = 1;
+    while ((1ull << nbits) < 2ull * (uint64_t)N + (uint64_t)nb + 1ull) nbits++;
+    ProfScope prof(PC_SUBSAMPLE, st, 15 + 5 * ((nbits + 7) / 8));
     PCRCG_TRY(cloud_starts(lens, nb, s.starts, st));
     k_bbox_init<<<(nb * 6 + 255) / 256, 256, 0, st>>>(s.bbox, nb);
     k_bbox<<<gb, 256, 0, st>>>(pts, N, s.starts, nb, s.bbox);
@@ -322,8 +325,6 @@ int subsample_batch_dev(const float* pts, int64_t n, const int32_t* lens, int32_
     PCRCG_CUDA(cudaMemsetAsync(s.rep, 0xff, sizeof(uint32_t) * (2 * (size_t)N + nb), st));
     k_insert<<<gb, 256, 0, st>>>(s.keys, N, s.starts, nb, s.rep, s.slot, s.iota);
     PCRCG_CUDA(cudaGetLastError());
-    int nbits = 1;
-    while ((1ull << nbits) < 2ull * (uint64_t)N + (uint64_t)nb + 1ull) nbits++;
     PCRCG_TRY(radix_sort_pairs(s.slot, s.iota, s.sslot, s.sidx, N, nbits, s.prim, s.prim_bytes, st));
     PCRCG_CUDA(cudaMemsetAsync(s.rank, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
     k_heads<<<gb, 256, 0, st>>>(s.sslot, s.sidx, N, s.rank);

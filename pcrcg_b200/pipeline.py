@@ -1,0 +1,82 @@
+"""The hot path end to end, as one object: stacked fragment pairs in -> encoder features out.
+
+    subsample x3 + radius search x10  (collate_fn_descriptor, datasets/dataloader.py:239-359)
+    -> 11 encoder blocks               (KPFCNN.forward encoder loop, models/architectures.py:520-524)
+
+``run_device`` keeps everything in HBM; ``run_host`` is the user-facing call with HOST buffers
+(pinned host -> device copy of the raw points, device -> host copy of the per-point features of
+the coarsest level), which is what bench.py times for its ``e2e`` figure.
+"""
+import numpy as np
+import torch
+
+from . import blocks, dataloader
+
+# neighbourhood limits frozen with the reference's calibration rule (datasets/dataloader.py:402-434,
+# keep_ratio 0.8) run through the reference C++ core on the synthetic families of synthetic.py
+CALIBRATED_LIMITS = {
+    "3dmatch_synthetic": [34, 39, 39, 38],
+    "3dlomatch_synthetic": [33, 40, 42, 40],
+    "3dmatch_lattice_synthetic": [34, 39, 41, 39],
+    "kitti_synthetic": [102, 102, 99, 91],
+    "3dmatch_demo_pair": [38, 36, 36, 38],      # SURVEY.md section 0.7 (widely used 3DMatch setting)
+}
+
+
+def init_kernel_points(net, seed=0):
+    """Deterministic stand-in for kernels/kernel_points.py:388-470 when no checkpoint is loaded:
+    centre point + 14 points near the sphere of radius 0.66*conv radius (random-init weights of the
+    named architecture; a real run loads them from the reference state_dict)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, blocks.KPConv):
+            d = torch.randn(m.K, 3, generator=g)
+            d = d / d.norm(dim=1, keepdim=True) * 0.66
+            d[0] = 0
+            m.set_kernel_points((d + 0.01 * torch.randn(m.K, 3, generator=g)) * m.radius)
+    return net
+
+
+class FeaturePath:
+    def __init__(self, config=None, limits=None, device="cuda", state_dict=None, seed=0):
+        self.config = config if config is not None else blocks.indoor_config()
+        self.limits = list(limits if limits is not None else CALIBRATED_LIMITS["3dmatch_synthetic"])
+        self.device = torch.device(device)
+        torch.manual_seed(seed)
+        self.encoder = blocks.KPEncoder(self.config)
+        if state_dict is not None:
+            self.encoder.load_reference(state_dict)
+        else:
+            init_kernel_points(self.encoder, seed)
+        self.encoder.to(self.device).eval()
+
+    @torch.no_grad()
+    def run_device(self, points, lengths, features=None):
+        """points [N,3] f32 cuda, lengths [2P] i32 cuda -> (features of the coarsest level [N3, C], batch dict)"""
+        batch = dataloader.build_pyramid(points, lengths, self.config, self.limits, device=self.device)
+        if features is None:
+            features = torch.ones((points.shape[0], self.config.in_feats_dim), dtype=torch.float32, device=self.device)
+        return self.encoder(features, batch), batch
+
+    @torch.no_grad()
+    def run_host(self, points_host, lengths_host, out_host=None):
+        """HOST buffers in and out.  points_host [N,3] f32 (pinned for async copies), lengths_host [2P] i32.
+        Returns (features_host [N3,C], lengths of the coarsest level [2P] on the host)."""
+        pts = points_host.to(self.device, non_blocking=True)
+        lens = lengths_host.to(self.device, non_blocking=True)
+        y, batch = self.run_device(pts, lens)
+        if out_host is not None and out_host.shape[0] >= y.shape[0]:
+            out = out_host[:y.shape[0]]
+            out.copy_(y, non_blocking=True)
+        else:
+            out = y.cpu()
+        coarse = batch["stack_lengths"][-1].cpu()
+        torch.cuda.current_stream().synchronize()
+        return out, coarse
+
+
+def stack_pairs(pairs):
+    """[(src, tgt), ...] -> (points [N,3] f32, lengths [2P] i32) NumPy, in the reference's src,tgt order."""
+    pts = np.concatenate([np.concatenate([s, t]) for s, t in pairs]).astype(np.float32)
+    lens = np.array([len(c) for p in pairs for c in p], np.int32)
+    return pts, lens
