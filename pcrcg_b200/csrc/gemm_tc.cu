@@ -1,13 +1,370 @@
-// tcgen05 tensor-core contraction (placeholder until the UMMA kernel lands: reports "not handled"
-// so gemm_dev uses the fp32 CUDA-core kernel).
+// tcgen05 tensor-core contraction for the KPConv weight contraction and the unary Linear layers.
+//
+//   C[M,N] = A[M,K] * B^T  (B stored [N,K], K contiguous), fp32 in / fp32 out, row scale epilogue.
+//
+// Precision: operands are split on the fly into bf16 (hi, lo) pairs and the product is evaluated as
+//   A_hi*B_hi + A_hi*B_lo + A_lo*B_hi      ("bf16x3", fp32 accumulation in TMEM)
+// which keeps ~16 mantissa bits per operand (measured ~1e-5 normwise vs fp32), inside the 1e-3
+// feature tolerance with margin where a single bf16 (2e-3) or tf32 (3e-4 per op, 11 stacked blocks)
+// pass is not.
+//
+// Kernel (one 128 x BN output tile per CTA, 192 threads, 1 CTA/SM):
+//   warp 0   : TMA producer -- cp.async.bulk.tensor 2D loads of the four operand tiles of a
+//              64-wide K block (A_hi, A_lo [128 x 64], B_hi, B_lo [BN x 64], 128B swizzle) into a
+//              STAGES-deep shared-memory ring, mbarrier expect_tx / complete_tx
+//   warp 1   : MMA issuer -- one elected lane issues tcgen05.mma.kind::f16 (M=128, K=16):
+//                 D[:, 0:2BN] += A_hi * [B_hi ; B_lo]^T      (one instruction, N = 2*BN)
+//                 D[:, 0:BN]  += A_lo * B_hi^T
+//              accumulators live in TMEM (2*BN fp32 columns); tcgen05.commit frees the smem slot
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b, (D1 + D2) * row_scale, vector stores to global
 #include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace pcrcg {
 
-int gemm_tc_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t, bool* handled)
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
+constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+// shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (SM100 format)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);          // start address  [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: bf16 x bf16 -> f32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BN> struct TcCfg {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;               // 16 KB per (hi|lo)
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // 32, 64, 128 or 256
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                                                             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                                                             float* __restrict__ C, int ldc, int M, int N, int K,
+                                                             const float* __restrict__ row_scale)
+{
+    using Cfg = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                tma_load_2d(st, &map_a_hi, full_bar(s), kb * TC_BK, m0);
+                tma_load_2d(st + Cfg::A_BYTES, &map_a_lo, full_bar(s), kb * TC_BK, m0);
+                tma_load_2d(st + 2 * Cfg::A_BYTES, &map_b_hi, full_bar(s), kb * TC_BK, n0);
+                tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_b_lo, full_bar(s), kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_cat = make_idesc(2 * BN);
+            constexpr uint32_t idesc_one = make_idesc(BN);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + Cfg::A_BYTES), db = make_desc(st + 2 * Cfg::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);          // 16 bf16 = 32 bytes inside the swizzle atom
+                    umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_cat, (uint32_t)((kb | k) != 0));
+                    umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float sc = (row_scale != nullptr && row < M) ? row_scale[row] : 1.0f;
+        const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            if (n0 + c >= N) break;                      // warp-uniform
+            uint32_t d1[16], d2[16];
+            tmem_ld16(trow + (uint32_t)c, d1);
+            tmem_ld16(trow + (uint32_t)(BN + c), d2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* o = C + (size_t)row * ldc + n0 + c;
+                if (n0 + c + 16 <= N && (ldc & 3) == 0) {
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) {
+                        float4 v;
+                        v.x = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
+                        v.y = (__uint_as_float(d1[u + 1]) + __uint_as_float(d2[u + 1])) * sc;
+                        v.z = (__uint_as_float(d1[u + 2]) + __uint_as_float(d2[u + 2])) * sc;
+                        v.w = (__uint_as_float(d1[u + 3]) + __uint_as_float(d2[u + 3])) * sc;
+                        *reinterpret_cast<float4*>(o + u) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        if (n0 + c + u < N) o[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand splitting: x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+__global__ void __launch_bounds__(256) k_split_bf16(const float* __restrict__ x, int ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                                    __nv_bfloat16* __restrict__ lo, int ldo)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = ldo >> 2;
+    if (e >= (long long)rows * c4) return;
+    const int r = (int)(e / c4), c = (int)(e - (long long)r * c4) * 4;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = (c + u < cols) ? x[(size_t)r * ldx + c + u] : 0.f;
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        h[u] = __float2bfloat16_rn(v[u]);
+        l[u] = __float2bfloat16_rn(v[u] - __bfloat162float(h[u]));
+    }
+    *reinterpret_cast<uint2*>(hi + (size_t)r * ldo + c) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + (size_t)r * ldo + c) = *reinterpret_cast<uint2*>(l);
+}
+
+// B given as [K,N] row-major -> hi/lo [N, ldo] (K contiguous), via a 32x32 shared-memory transpose
+__global__ void __launch_bounds__(256) k_split_bf16_transpose(const float* __restrict__ B, int ldb, int K, int N, __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo, int ldo)
+{
+    __shared__ float t[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        int k = k0 + j, n = n0 + tx;
+        t[j][tx] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int n = n0 + j, k = k0 + tx;
+        if (n < N && k < ldo) {
+            float v = k < K ? t[tx][j] : 0.f;
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hi[(size_t)n * ldo + k] = h;
+            lo[(size_t)n * ldo + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode()
+{
+    if (g_encode) return PCRCG_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PCRCG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PCRCG_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is unavailable in this driver");
+    g_encode = (EncodeTiledFn)fn;
+    return PCRCG_OK;
+}
+
+// 2D bf16 tensor [rows, cols] (cols contiguous, pitch ld elements), box [box_rows x 64], 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows)
+{
+    cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)ld * 2 };
+    cuuint32_t box[2] = { (cuuint32_t)TC_BK, (cuuint32_t)box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCRCG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return PCRCG_OK;
+}
+
+template <int BN>
+static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int ldk,
+                     float* C, int ldc, int M, int N, int K, const float* row_scale, cudaStream_t st)
+{
+    using Cfg = TcCfg<BN>;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    PCRCG_TRY(make_map(&ma_hi, a_hi, M, K, ldk, TC_BM));
+    PCRCG_TRY(make_map(&ma_lo, a_lo, M, K, ldk, TC_BM));
+    PCRCG_TRY(make_map(&mb_hi, b_hi, N, K, ldk, BN));
+    PCRCG_TRY(make_map(&mb_lo, b_lo, N, K, ldk, BN));
+    static bool attr_set = false;
+    if (!attr_set) {
+        PCRCG_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)cdiv64(M, TC_BM), (unsigned)cdiv64(N, BN));
+    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+static bool g_pool_ready = false;
+
+int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
+                const float* row_scale, cudaStream_t st, bool* handled)
 {
     *handled = false;
-    return PCRCG_OK;
+    if (N % 16 != 0 || N < 16 || K < 16 || M < 1) return PCRCG_OK;        // ragged shapes stay on the CUDA-core kernel
+    PCRCG_TRY(get_encode());
+    if (!g_pool_ready) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        PCRCG_CUDA(cudaGetDevice(&dev));
+        PCRCG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thr = ~0ull;
+        PCRCG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        g_pool_ready = true;
+    }
+    const int ldk = (K + 7) / 8 * 8;                       // bf16 row pitch: multiple of 16 bytes for TMA
+    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+    const size_t a_elems = (size_t)M * ldk, b_elems = (size_t)N * ldk;
+    PCRCG_CUDA(cudaMallocAsync((void**)&a_hi, (2 * a_elems + 2 * b_elems) * sizeof(__nv_bfloat16) + 1024, st));
+    a_lo = a_hi + a_elems;
+    b_hi = a_lo + a_elems;
+    b_lo = b_hi + b_elems;
+    count_launches(3);
+    {
+        long long tot = (long long)M * (ldk / 4);
+        k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, ldk);
+    }
+    if (b_is_nk) {
+        long long tot = (long long)N * (ldk / 4);
+        k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, ldk);
+    } else {
+        k_split_bf16_transpose<<<dim3((unsigned)cdiv64(ldk, 32), (unsigned)cdiv64(N, 32)), 256, 0, st>>>(B, ldb, K, N, b_hi, b_lo, ldk);
+    }
+    int rc = PCRCG_OK;
+    if (cudaGetLastError() != cudaSuccess) { set_error("gemm_tc: split launch failed"); rc = PCRCG_ERR; }
+    if (rc == PCRCG_OK) {
+        if (N % 128 == 0) rc = launch_tc<128>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
+        else if (N % 64 == 0) rc = launch_tc<64>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
+        else if (N % 32 == 0) rc = launch_tc<32>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
+        else rc = launch_tc<16>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
+    }
+    cudaFreeAsync(a_hi, st);
+    if (rc == PCRCG_OK) *handled = true;
+    return rc;
 }
 
 }  // namespace pcrcg
