@@ -11,40 +11,60 @@
 namespace pcrcg {
 
 // ---- column statistics: mean / rstd per (segment, column) ----------------------------------------
-// grid (ceil(C/32), nseg), block 32 x 8 : two passes over the segment's rows (L2 resident).
-__global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ x, int ldx, int C, const int32_t* __restrict__ seg_starts,
-                                                  float eps, float* __restrict__ mean, float* __restrict__ rstd)
+// Pass 1: each block reduces CS_ROWS consecutive rows x 32 columns (one coalesced read of x) and adds
+// its partial sum / sum of squares in fp64 to the segment's accumulators; a block that straddles a
+// segment boundary flushes once per segment.  Pass 2 turns them into mean and rsqrt(var + eps)
+// (biased variance, E[x^2] - mean^2 evaluated in fp64).
+constexpr int CS_ROWS = 512;
+
+__global__ void __launch_bounds__(256) k_colstats_partial(const float* __restrict__ x, int ldx, int n, int C,
+                                                          const int32_t* __restrict__ seg_starts, int nseg, double* __restrict__ acc)
 {
-    __shared__ float red[8][33];
+    __shared__ double red[2][8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx, seg = blockIdx.y;
-    const int r0 = seg_starts[seg], r1 = seg_starts[seg + 1];
+    const int c = blockIdx.x * 32 + tx;
     const bool ok = c < C;
-    float s = 0.f;
-    for (int r = r0 + ty; r < r1; r += 8) s += ok ? x[(size_t)r * ldx + c] : 0.f;
-    red[ty][tx] = s;
-    __syncthreads();
-    float tot = 0.f;
+    int r = blockIdx.y * CS_ROWS;
+    const int rend = min(n, r + CS_ROWS);
+    int seg = nseg > 1 ? cloud_of(seg_starts, nseg, r) : 0;
+    while (r < rend) {
+        const int stop = min(rend, seg_starts[seg + 1]);
+        float s = 0.f, s2 = 0.f;                      // <= 64 rows per thread: fp32 partials are safe
+        for (int i = r + ty; i < stop; i += 8) {
+            float v = ok ? x[(size_t)i * ldx + c] : 0.f;
+            s += v;
+            s2 = fmaf(v, v, s2);
+        }
+        red[0][ty][tx] = (double)s;
+        red[1][ty][tx] = (double)s2;
+        __syncthreads();
+        if (ty < 2 && ok) {
+            double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) tot += red[k][tx];
-    const float n = (float)(r1 - r0);
-    const float mu = n > 0.f ? tot / n : 0.f;
-    __syncthreads();
-    float v = 0.f;
-    for (int r = r0 + ty; r < r1; r += 8) {
-        float d = ok ? x[(size_t)r * ldx + c] - mu : 0.f;
-        v = fmaf(d, d, v);
+            for (int k = 0; k < 8; k++) t += red[ty][k][tx];
+            atomicAdd(acc + ((size_t)seg * 2 + ty) * C + c, t);
+        }
+        __syncthreads();
+        r = stop;
+        seg++;
     }
-    red[ty][tx] = v;
-    __syncthreads();
-    if (ty == 0 && ok) {
-        float var = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; k++) var += red[k][tx];
-        var = n > 0.f ? var / n : 0.f;
-        mean[(size_t)seg * C + c] = mu;
-        rstd[(size_t)seg * C + c] = rsqrtf(var + eps);
+}
+
+__global__ void __launch_bounds__(256) k_colstats_final(const double* __restrict__ acc, const int32_t* __restrict__ seg_starts, int nseg,
+                                                        int C, float eps, float* __restrict__ mean, float* __restrict__ rstd)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nseg * C) return;
+    const int seg = e / C, c = e - seg * C;
+    const double n = (double)(seg_starts[seg + 1] - seg_starts[seg]);
+    double mu = 0.0, var = 0.0;
+    if (n > 0) {
+        mu = acc[((size_t)seg * 2 + 0) * C + c] / n;
+        var = acc[((size_t)seg * 2 + 1) * C + c] / n - mu * mu;
+        if (var < 0.0) var = 0.0;
     }
+    mean[e] = (float)mu;
+    rstd[e] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // out = act( (x - mean)*rstd  [ + (sc - sc_mean)*sc_rstd | + sc ] ),  act = LeakyReLU(slope) if slope >= 0
@@ -113,11 +133,17 @@ __global__ void __launch_bounds__(256) k_closest_pool(const float* __restrict__ 
 int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,
                  cudaStream_t st)
 {
-    (void)n;
-    PCRCG_REQUIRE(C >= 1 && nseg >= 1 && nseg < 65536, "instance norm: bad dimensions");
-    ProfScope prof(PC_NORM, st, 1);
-    k_colstats<<<dim3((unsigned)cdiv64(C, 32), (unsigned)nseg), 256, 0, st>>>(x, C, C, seg_starts, eps, mean, rstd);
-    PCRCG_CUDA(cudaGetLastError());
+    PCRCG_REQUIRE(C >= 1 && nseg >= 1 && nseg < 65536 && n < (1ll << 31), "instance norm: bad dimensions");
+    ProfScope prof(PC_NORM, st, 2);
+    double* acc = nullptr;
+    const size_t acc_bytes = (size_t)nseg * 2 * C * sizeof(double);
+    PCRCG_CUDA(cudaMallocAsync((void**)&acc, acc_bytes, st));
+    PCRCG_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, st));
+    if (n > 0) k_colstats_partial<<<dim3((unsigned)cdiv64(C, 32), (unsigned)cdiv64(n, CS_ROWS)), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, acc);
+    k_colstats_final<<<(unsigned)cdiv64((int64_t)nseg * C, 256), 256, 0, st>>>(acc, seg_starts, nseg, C, eps, mean, rstd);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(acc, st);
+    PCRCG_CUDA(e);
     return PCRCG_OK;
 }
 

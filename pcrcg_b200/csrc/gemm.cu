@@ -85,6 +85,7 @@ int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, f
 
 static int g_force_simt = 0;
 void gemm_set_force_simt(int v) { g_force_simt = v; }
+int gemm_force_simt_get() { return g_force_simt; }
 
 int gemm_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
              const float* row_scale, cudaStream_t st)

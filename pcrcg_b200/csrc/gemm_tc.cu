@@ -321,33 +321,35 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
 
 static bool g_pool_ready = false;
 
-int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
-                const float* row_scale, cudaStream_t st, bool* handled)
+static int pool_setup()
 {
-    *handled = false;
-    if (N % 16 != 0 || N < 16 || K < 16 || M < 1) return PCRCG_OK;        // ragged shapes stay on the CUDA-core kernel
+    if (g_pool_ready) return PCRCG_OK;
+    int dev = 0;
+    cudaMemPool_t pool;
+    PCRCG_CUDA(cudaGetDevice(&dev));
+    PCRCG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = ~0ull;
+    PCRCG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    g_pool_ready = true;
+    return PCRCG_OK;
+}
+
+bool gemm_tc_shape_ok(int M, int N, int K) { return N % 16 == 0 && N >= 16 && K >= 16 && M >= 1; }
+
+// A already split: a_hi / a_lo bf16 [M, ldk] (ldk % 8 == 0).  B fp32, split here (weights are small).
+int gemm_tc_presplit_dev(const void* a_hi_v, const void* a_lo_v, int ldk, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M,
+                         int N, int K, const float* row_scale, cudaStream_t st)
+{
+    PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
     PCRCG_TRY(get_encode());
-    if (!g_pool_ready) {
-        int dev = 0;
-        cudaMemPool_t pool;
-        PCRCG_CUDA(cudaGetDevice(&dev));
-        PCRCG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t thr = ~0ull;
-        PCRCG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        g_pool_ready = true;
-    }
-    const int ldk = (K + 7) / 8 * 8;                       // bf16 row pitch: multiple of 16 bytes for TMA
-    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
-    const size_t a_elems = (size_t)M * ldk, b_elems = (size_t)N * ldk;
-    PCRCG_CUDA(cudaMallocAsync((void**)&a_hi, (2 * a_elems + 2 * b_elems) * sizeof(__nv_bfloat16) + 1024, st));
-    a_lo = a_hi + a_elems;
-    b_hi = a_lo + a_elems;
+    PCRCG_TRY(pool_setup());
+    const __nv_bfloat16* a_hi = (const __nv_bfloat16*)a_hi_v;
+    const __nv_bfloat16* a_lo = (const __nv_bfloat16*)a_lo_v;
+    __nv_bfloat16 *b_hi = nullptr, *b_lo = nullptr;
+    const size_t b_elems = (size_t)N * ldk;
+    PCRCG_CUDA(cudaMallocAsync((void**)&b_hi, 2 * b_elems * sizeof(__nv_bfloat16) + 1024, st));
     b_lo = b_hi + b_elems;
-    count_launches(3);
-    {
-        long long tot = (long long)M * (ldk / 4);
-        k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, ldk);
-    }
+    count_launches(2);
     if (b_is_nk) {
         long long tot = (long long)N * (ldk / 4);
         k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, ldk);
@@ -362,6 +364,27 @@ int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, f
         else if (N % 32 == 0) rc = launch_tc<32>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
         else rc = launch_tc<16>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
     }
+    cudaFreeAsync(b_hi, st);
+    return rc;
+}
+
+int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
+                const float* row_scale, cudaStream_t st, bool* handled)
+{
+    *handled = false;
+    if (!gemm_tc_shape_ok(M, N, K)) return PCRCG_OK;        // ragged shapes stay on the CUDA-core kernel
+    PCRCG_TRY(pool_setup());
+    const int ldk = (K + 7) / 8 * 8;                       // bf16 row pitch: multiple of 16 bytes for TMA
+    __nv_bfloat16* a_hi = nullptr;
+    const size_t a_elems = (size_t)M * ldk;
+    PCRCG_CUDA(cudaMallocAsync((void**)&a_hi, 2 * a_elems * sizeof(__nv_bfloat16) + 1024, st));
+    __nv_bfloat16* a_lo = a_hi + a_elems;
+    count_launches(1);
+    long long tot = (long long)M * (ldk / 4);
+    k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(A, lda, M, K, a_hi, a_lo, ldk);
+    int rc = PCRCG_OK;
+    if (cudaGetLastError() != cudaSuccess) { set_error("gemm_tc: split launch failed"); rc = PCRCG_ERR; }
+    if (rc == PCRCG_OK) rc = gemm_tc_presplit_dev(a_hi, a_lo, ldk, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, st);
     cudaFreeAsync(a_hi, st);
     if (rc == PCRCG_OK) *handled = true;
     return rc;

