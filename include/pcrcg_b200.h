@@ -112,6 +112,25 @@ int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, 
 int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq,
                            int32_t idx_stride, float* out, pcrcg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Colour path.  pcrcg_projection_dev = projection.py:31-61 Projection.projection(points, depth_map,
+ * world2camera): index lists inds2d [M,2] (x,y) / inds3d [M] (ascending), int64, *count = M (device).
+ * world2camera / intrinsics: HOST pointers to 16 floats (row-major 4x4).  Outputs sized for n.
+ * pcrcg_project_scatter_dev = projection + the gather/scatter of models/architectures.py:273-307,
+ * 360-370 fused: out [n, C+1]; views are given in the reference's WRITE order (the last view that
+ * sees a point wins); view v applies to points [row_lo[v], row_hi[v]); unseen points get base[i]
+ * (1 when base is NULL) in every column.  depth / feat ([C,H,W]) / valid ([H,W], entries may be
+ * NULL) are HOST arrays of DEVICE pointers; w2c / k4 HOST arrays of nviews x 16 floats.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcrcg_projection_ws_bytes(int64_t n);
+int pcrcg_projection_dev(const float* points, int64_t n, const float* depth, int32_t H, int32_t W, const float* world2camera,
+                         const float* intrinsics, float thresh, int64_t* inds2d, int64_t* inds3d, int32_t* count, void* ws,
+                         size_t ws_bytes, pcrcg_stream_t stream);
+int pcrcg_project_scatter_dev(const float* points, int64_t n, int32_t nviews, const float* const* depth, const float* const* feat,
+                              const float* const* valid, const float* w2c, const float* k4, const int32_t* row_lo,
+                              const int32_t* row_hi, int32_t H, int32_t W, int32_t C, float thresh, const float* base, float* out,
+                              pcrcg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,12 @@ int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const 
 int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
+size_t projection_ws_bytes(int64_t n);
+int projection_dev(const float*, int64_t, const float*, int32_t, int32_t, const float*, const float*, float, long long*, long long*, int32_t*,
+                   void*, size_t, cudaStream_t);
+int project_scatter_dev(const float*, int64_t, int32_t, const float* const*, const float* const*, const float* const*, const float*,
+                        const float*, const int32_t*, const int32_t*, int32_t, int32_t, int32_t, float, const float*, float*, cudaStream_t);
+
 // RAII device buffer for the host entry points
 struct DevBuf {
     void* p = nullptr;
@@ -235,6 +241,24 @@ int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* in
                            float* out, pcrcg_stream_t stream)
 {
     return closest_pool_dev(x, ns, C, inds, idx_is_i64, nq, idx_stride, out, (cudaStream_t)stream);
+}
+
+size_t pcrcg_projection_ws_bytes(int64_t n) { return projection_ws_bytes(n); }
+
+int pcrcg_projection_dev(const float* points, int64_t n, const float* depth, int32_t H, int32_t W, const float* world2camera,
+                         const float* intrinsics, float thresh, int64_t* inds2d, int64_t* inds3d, int32_t* count, void* ws, size_t ws_bytes,
+                         pcrcg_stream_t stream)
+{
+    return projection_dev(points, n, depth, H, W, world2camera, intrinsics, thresh, (long long*)inds2d, (long long*)inds3d, count, ws,
+                          ws_bytes, (cudaStream_t)stream);
+}
+
+int pcrcg_project_scatter_dev(const float* points, int64_t n, int32_t nviews, const float* const* depth, const float* const* feat,
+                              const float* const* valid, const float* w2c, const float* k4, const int32_t* row_lo, const int32_t* row_hi,
+                              int32_t H, int32_t W, int32_t C, float thresh, const float* base, float* out, pcrcg_stream_t stream)
+{
+    return project_scatter_dev(points, n, nviews, depth, feat, valid, w2c, k4, row_lo, row_hi, H, W, C, thresh, base, out,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,87 @@
+"""Colour path: ``projection.py`` of the reference (class ``Projection``) and the un-projection of
+2D image features onto the 3D points (``models/architectures.py:273-307,360-370``), on the GPU.
+
+``Projection(intrinsic_matrix, thresh).projection(points, depth_map, world2camera)`` keeps the
+reference's signature and return values (``inds2d`` LongTensor [M,2] in (x, y) order, ``inds3d``
+LongTensor [M], ascending), returned on the device the points came from.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import lib, check
+from .ops import _f32c, _stream, _ws
+
+
+def _mat16(m):
+    m = torch.as_tensor(m, dtype=torch.float32).detach().cpu()
+    if tuple(m.shape) == (3, 3):                      # projection.py:22-25
+        e = torch.eye(4)
+        e[:3, :3] = m
+        m = e
+    return np.ascontiguousarray(m.numpy().reshape(16), dtype=np.float32)
+
+
+class Projection(object):
+    def __init__(self, intrinsic_matrix=0, thresh=0.1, device="cuda"):
+        self.intrinsics = intrinsic_matrix
+        self.thresh = thresh
+        self.device = torch.device(device)
+
+    def projection(self, points, depth_map, world2camera):
+        src_dev = points.device if torch.is_tensor(points) else torch.device("cpu")
+        dev = src_dev if src_dev.type == "cuda" else self.device
+        pts = _f32c(torch.as_tensor(points).to(dev))
+        depth = _f32c(torch.as_tensor(depth_map).to(dev))
+        depth = depth.reshape(depth.shape[-2], depth.shape[-1])          # projection.py:41 squeeze(0)
+        H, W = depth.shape
+        n = pts.shape[0]
+        k4, w2c = _mat16(self.intrinsics), _mat16(world2camera)
+        L = lib()
+        with torch.cuda.device(dev):
+            i2 = torch.empty((max(n, 1), 2), dtype=torch.int64, device=dev)
+            i3 = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            ws = _ws(L.pcrcg_projection_ws_bytes(n), dev)
+            check(L.pcrcg_projection_dev(pts.data_ptr(), n, depth.data_ptr(), H, W, w2c.ctypes.data, k4.ctypes.data, float(self.thresh),
+                                         i2.data_ptr(), i3.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+            m = int(cnt.item())
+        return i2[:m].to(src_dev), i3[:m].to(src_dev)
+
+
+def unproject_features(points, views, base=None, thresh=0.1):
+    """Fused projection + feature gather + scatter.
+
+    points [N,3] cuda; views: list in the reference's WRITE order (e.g. src image 2, src image 1,
+    tgt image 2, tgt image 1) of dicts with ``depth`` [H,W], ``world2camera`` [4,4], ``intrinsics``
+    [4,4], ``feature2d`` [C,H,W] (cuda), optional ``valid_map`` [H,W], and ``rows`` = (lo, hi): the
+    range of point rows (the cloud) the view belongs to.  Returns x [N, C+1]."""
+    pts = _f32c(points)
+    dev = pts.device
+    n = pts.shape[0]
+    nv = len(views)
+    keep = []
+    dptr, fptr, vptr = (C.c_void_p * nv)(), (C.c_void_p * nv)(), (C.c_void_p * nv)()
+    w2c = np.zeros((nv, 16), np.float32)
+    k4 = np.zeros((nv, 16), np.float32)
+    lo, hi = np.zeros(nv, np.int32), np.zeros(nv, np.int32)
+    Cc = H = W = None
+    for v, view in enumerate(views):
+        d = _f32c(torch.as_tensor(view["depth"]).to(dev))
+        d = d.reshape(d.shape[-2], d.shape[-1])
+        f = _f32c(torch.as_tensor(view["feature2d"]).to(dev))
+        vm = view.get("valid_map")
+        vm = _f32c(torch.as_tensor(vm).to(dev)) if vm is not None else None
+        keep += [d, f, vm]
+        Cc, H, W = f.shape
+        dptr[v], fptr[v], vptr[v] = d.data_ptr(), f.data_ptr(), (vm.data_ptr() if vm is not None else None)
+        w2c[v], k4[v] = _mat16(view["world2camera"]), _mat16(view["intrinsics"])
+        lo[v], hi[v] = view.get("rows", (0, n))
+    out = torch.empty((n, Cc + 1), dtype=torch.float32, device=dev)
+    b = _f32c(base.reshape(-1)) if base is not None else None
+    with torch.cuda.device(dev):
+        check(lib().pcrcg_project_scatter_dev(pts.data_ptr(), n, nv, dptr, fptr, vptr, w2c.ctypes.data, k4.ctypes.data, lo.ctypes.data,
+                                              hi.ctypes.data, H, W, Cc, float(thresh), b.data_ptr() if b is not None else None,
+                                              out.data_ptr(), _stream()))
+    return out
