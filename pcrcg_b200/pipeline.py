@@ -80,3 +80,13 @@ def stack_pairs(pairs):
     pts = np.concatenate([np.concatenate([s, t]) for s, t in pairs]).astype(np.float32)
     lens = np.array([len(c) for p in pairs for c in p], np.int32)
     return pts, lens
+
+
+def per_pair_features(path, pairs):
+    """compute() for sharding.run_sharded: runs one stacked batch and splits the coarsest-level
+    features back into per-pair tensors."""
+    pts, lens = stack_pairs(pairs)
+    dev = path.device
+    y, batch = path.run_device(torch.from_numpy(pts).to(dev), torch.from_numpy(lens).to(dev))
+    seg = batch["pair_segments"][-1].cpu().tolist()
+    return [y[seg[k]:seg[k + 1]] for k in range(len(pairs))]

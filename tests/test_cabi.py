@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads, exports every symbol include/pcrcg_b200.h declares, and the Python
+binding table matches the header.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pcrcg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcrcg_[a-z0-9_]+)\s*\(", src)) - {"pcrcg_stream_t"})
+
+
+def test_header_symbols_exported():
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    lib = ctypes.CDLL(g.LIB)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pcrcg_b200.h but not exported"
+
+
+def test_binding_table_matches_header():
+    from pcrcg_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    L = _lib.lib()
+    assert L.pcrcg_version() >= 100
+    assert L.pcrcg_subsample_ws_bytes(1000, 2) > 0 and L.pcrcg_radius_ws_bytes(1000, 1000, 2) > 0
+    assert L.pcrcg_profile_classes() == 8 and L.pcrcg_profile_class_name(4) == b"gemm"
+
+
+def test_no_oracle_in_product_path():
+    """The product package must never import the CPU checker."""
+    pkg = os.path.join(ROOT, "pcrcg_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports oracle"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from pcrcg_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from pcrcg_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors required"):
+        ops.subsample_batch(torch.zeros(4, 3), torch.tensor([4], dtype=torch.int32), 0.1)
+    with pytest.raises(RuntimeError, match="CUDA tensors required"):
+        ops.kpconv_forward(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 2, dtype=torch.int64), torch.zeros(4, 1),
+                           torch.zeros(15, 3), torch.zeros(15, 1, 8), 0.05)
