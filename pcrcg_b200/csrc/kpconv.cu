@@ -45,12 +45,15 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
     const int c0 = blockIdx.y * (CJ * 32);                  // channel slab of this block
     if (n >= nq) return;
 
-    // kernel point of this lane (lanes 0..K-1 and 16..16+K-1 serve two neighbours per iteration)
-    const int kl = lane & 15;
+    // lanes 0..14 / 16..30 hold kernel point kl for the neighbour of their half-warp; lanes 15 / 31 are
+    // spare and read the neighbour's "row sum > 0" flag.  (s - q) - kp is evaluated as s - (q + kp).
+    const int kl = lane & 15, half = lane >> 4;
     float kx = 0.f, ky = 0.f, kz = 0.f;
-    if (kl < K) { kx = kpts[3 * kl]; ky = kpts[3 * kl + 1]; kz = kpts[3 * kl + 2]; }
-    const float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
-
+    if (kl < K) {
+        kx = kpts[3 * kl] + q_pts[3 * (size_t)n];
+        ky = kpts[3 * kl + 1] + q_pts[3 * (size_t)n + 1];
+        kz = kpts[3 * kl + 2] + q_pts[3 * (size_t)n + 2];
+    }
     float acc[KP_MAX - 1][CJ];
 #pragma unroll
     for (int k = 0; k < KP_MAX - 1; k++)
@@ -59,39 +62,51 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
     int cnt = 0;
 
     const IdxT* row = idx + (size_t)n * idx_stride;
+    const float* xc = x + c0 + lane;
+    bool cok[CJ];
+#pragma unroll
+    for (int jj = 0; jj < CJ; jj++) cok[jj] = c0 + jj * 32 + lane < cin;
+    float* sw = &s_w[w][half][kl];
+    const float4* wv0 = reinterpret_cast<const float4*>(s_w[w][0]);
+    const float4* wv1 = reinterpret_cast<const float4*>(s_w[w][1]);
+
     for (int h0 = 0; h0 < H; h0 += 2) {
-        // lanes 0..15 -> neighbour h0, lanes 16..31 -> neighbour h0+1
-        const int hh = h0 + (lane >> 4);
-        long long jn = hh < H ? (long long)row[hh] : (long long)ns;
-        const bool valid = jn >= 0 && jn < ns;
+        const int hh = h0 + half;
+        int jn = ns;
+        if (hh < H) { long long t = (long long)row[hh]; jn = (t >= 0 && t < ns) ? (int)t : ns; }
+        const bool valid = jn < ns;
         float wgt = 0.f;
-        if (valid && kl < K) {
-            float dx = s_pts[3 * (size_t)jn] - qx - kx, dy = s_pts[3 * (size_t)jn + 1] - qy - ky,
-                  dz = s_pts[3 * (size_t)jn + 2] - qz - kz;
-            wgt = fmaxf(0.f, 1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_extent);
+        bool pos = false;
+        if (valid) {
+            if (kl < K) {
+                const float* sp = s_pts + 3 * (size_t)(unsigned)jn;
+                const float dx = sp[0] - kx, dy = sp[1] - ky, dz = sp[2] - kz;
+                const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
+                wgt = fmaxf(0.f, fmaf(-d2 * rsqrtf(d2), inv_extent, 1.f));
+            } else if (kl == 15) {
+                pos = rowflag[jn] != 0;
+            }
         }
-        s_w[w][lane >> 4][kl] = wgt;
-        const long long j0 = __shfl_sync(0xffffffffu, jn, 0), j1 = __shfl_sync(0xffffffffu, jn, 16);
+        *sw = wgt;
+        cnt += __popc(__ballot_sync(0xffffffffu, pos));
+        const int j0 = __shfl_sync(0xffffffffu, jn, 0), j1 = __shfl_sync(0xffffffffu, jn, 16);
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 2; t++) {
-            const long long j = t == 0 ? j0 : j1;
-            if (j < 0 || j >= ns) continue;            // shadow neighbour: zero weights, zero features
-            if (blockIdx.y == 0) cnt += rowflag[j];
+            const int j = t == 0 ? j0 : j1;
+            if (j >= ns) continue;                     // shadow neighbour: zero weights, zero features (warp-uniform)
+            const float* xr = xc + (size_t)((unsigned)j * (unsigned)ldx);
             float f[CJ];
 #pragma unroll
-            for (int jj = 0; jj < CJ; jj++) {
-                int c = c0 + jj * 32 + lane;
-                f[jj] = c < cin ? __ldg(x + (size_t)j * ldx + c) : 0.f;
-            }
-            const float4* wv = reinterpret_cast<const float4*>(s_w[w][t]);
+            for (int jj = 0; jj < CJ; jj++) f[jj] = cok[jj] ? __ldg(xr + jj * 32) : 0.f;
+            const float4* wv = t == 0 ? wv0 : wv1;
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++) {
-                float4 ww = wv[k4];
-                float wk[4] = { ww.x, ww.y, ww.z, ww.w };
+                const float4 ww = wv[k4];
+                const float wk[4] = { ww.x, ww.y, ww.z, ww.w };
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    int k = k4 * 4 + u;
+                    const int k = k4 * 4 + u;
                     if (k < KP_MAX - 1) {
 #pragma unroll
                         for (int jj = 0; jj < CJ; jj++) acc[k][jj] = fmaf(wk[u], f[jj], acc[k][jj]);
@@ -102,20 +117,20 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
         __syncwarp();
     }
     // wf[n][k*cin + c]   (fp32, or split into bf16 hi/lo for the tensor-core contraction)
+    const size_t obase = (size_t)n * ldk + c0 + lane;
 #pragma unroll
     for (int k = 0; k < KP_MAX - 1; k++) {
         if (k < K) {
 #pragma unroll
             for (int jj = 0; jj < CJ; jj++) {
-                int c = c0 + jj * 32 + lane;
-                if (c < cin) {
+                if (cok[jj]) {
+                    const size_t e = obase + (size_t)k * cin + jj * 32;
                     if (SPLIT) {
-                        __nv_bfloat16 h = __float2bfloat16_rn(acc[k][jj]);
-                        size_t e = (size_t)n * ldk + (size_t)k * cin + c;
+                        const __nv_bfloat16 h = __float2bfloat16_rn(acc[k][jj]);
                         wf_hi[e] = h;
                         wf_lo[e] = __float2bfloat16_rn(acc[k][jj] - __bfloat162float(h));
                     } else {
-                        wf[(size_t)n * ldk + (size_t)k * cin + c] = acc[k][jj];
+                        wf[e] = acc[k][jj];
                     }
                 }
             }
@@ -124,6 +139,162 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate(
     if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core aggregation (cin % 8 == 0): per query point the [16 kernel points x H] influence matrix
+// times the gathered [H x channels] feature rows is evaluated with warp-level mma.sync m16n8k8 TF32,
+// operands split hi/lo ("3xTF32": hi*hi + hi*lo + lo*hi) so the result is fp32-accurate.
+//   M = kernel point (15 padded to 16), K = neighbour (8 per step), N = 8 channels per tile.
+//   Each lane computes exactly the 4 influence weights of its A fragment (kernel points g, g+8 x
+//   neighbours t, t+4 of the step) -- every (kernel point, neighbour) pair is evaluated once per warp
+//   and never leaves registers.  Channel c of tile nt, column g' is  c0 + g'*NT + nt, so a lane's B
+//   fragment values for all NT tiles are NT CONSECUTIVE floats of the neighbour's feature row
+//   (float4 gathers) and its D fragments cover 2*NT consecutive channels (vector stores).
+constexpr uint32_t TF32_MASK = 0xffffe000u;
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float influence(const float* __restrict__ sp, float kx, float ky, float kz, float inv_extent)
+{
+    const float dx = sp[0] - kx, dy = sp[1] - ky, dz = sp[2] - kz;
+    const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
+    return fmaxf(0.f, fmaf(-d2 * rsqrtf(d2), inv_extent, 1.f));
+}
+
+constexpr int MMA_KS = 5;            // k-steps (8 neighbours each) whose weight fragments are held in registers at once
+
+template <typename IdxT, int NT, bool SPLIT>
+__global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate_mma(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const float* __restrict__ x, int cin, int ldx, const uint8_t* __restrict__ rowflag,
+    const float* __restrict__ kpts, int K, float inv_extent, float* __restrict__ wf, __nv_bfloat16* __restrict__ wf_hi,
+    __nv_bfloat16* __restrict__ wf_lo, int ldk, float* __restrict__ inv_cnt)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * AGG_WARPS + w;
+    if (n >= nq) return;
+    const int g = lane >> 2, t = lane & 3;
+    const int c0 = blockIdx.y * (NT * 8);
+
+    const float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
+    const bool k1ok = g + 8 < K, k0ok = g < K;
+    const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
+    const float k0x = kpts[3 * ka] + qx, k0y = kpts[3 * ka + 1] + qy, k0z = kpts[3 * ka + 2] + qz;
+    const float k1x = kpts[3 * kb] + qx, k1y = kpts[3 * kb + 1] + qy, k1z = kpts[3 * kb + 2] + qz;
+
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    int cnt = 0;
+    const IdxT* row = idx + (size_t)n * idx_stride;
+    const float* xl = x + c0 + g * NT;                    // this lane's NT consecutive channels
+
+    for (int h0 = 0; h0 < H; h0 += MMA_KS * 8) {
+        uint32_t ahi[MMA_KS][4], alo[MMA_KS][4];
+        unsigned ja[MMA_KS], jb[MMA_KS];
+#pragma unroll
+        for (int s = 0; s < MMA_KS; s++) {
+            const int ha = h0 + 8 * s + t, hb = ha + 4;
+            long long ia = ha < H ? (long long)row[ha] : (long long)ns;
+            long long ib = hb < H ? (long long)row[hb] : (long long)ns;
+            const bool va = ia >= 0 && ia < ns, vb = ib >= 0 && ib < ns;
+            ja[s] = va ? (unsigned)ia : 0u;
+            jb[s] = vb ? (unsigned)ib : 0u;
+            const float* spa = s_pts + 3 * (size_t)ja[s];
+            const float* spb = s_pts + 3 * (size_t)jb[s];
+            float w00 = (va && k0ok) ? influence(spa, k0x, k0y, k0z, inv_extent) : 0.f;
+            float w10 = (va && k1ok) ? influence(spa, k1x, k1y, k1z, inv_extent) : 0.f;
+            float w01 = (vb && k0ok) ? influence(spb, k0x, k0y, k0z, inv_extent) : 0.f;
+            float w11 = (vb && k1ok) ? influence(spb, k1x, k1y, k1z, inv_extent) : 0.f;
+            const float wv[4] = { w00, w10, w01, w11 };
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t hi = __float_as_uint(wv[u]) & TF32_MASK;
+                ahi[s][u] = hi;
+                alo[s][u] = __float_as_uint(wv[u] - __uint_as_float(hi));
+            }
+            if (g == 0 && blockIdx.y == 0) cnt += (va ? (int)rowflag[ja[s]] : 0) + (vb ? (int)rowflag[jb[s]] : 0);
+        }
+#pragma unroll
+        for (int s = 0; s < MMA_KS; s++) {
+            if (h0 + 8 * s >= H) break;                    // warp-uniform
+            float fa[NT], fb[NT];
+            const float* ra = xl + (size_t)(ja[s] * (unsigned)ldx);
+            const float* rb = xl + (size_t)(jb[s] * (unsigned)ldx);
+            if (NT % 4 == 0) {
+#pragma unroll
+                for (int v = 0; v < NT / 4; v++) {
+                    const float4 A = __ldg(reinterpret_cast<const float4*>(ra) + v);
+                    const float4 B = __ldg(reinterpret_cast<const float4*>(rb) + v);
+                    fa[4 * v] = A.x; fa[4 * v + 1] = A.y; fa[4 * v + 2] = A.z; fa[4 * v + 3] = A.w;
+                    fb[4 * v] = B.x; fb[4 * v + 1] = B.y; fb[4 * v + 2] = B.z; fb[4 * v + 3] = B.w;
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NT; v++) { fa[v] = __ldg(ra + v); fb[v] = __ldg(rb + v); }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                const uint32_t b0h = __float_as_uint(fa[nt]) & TF32_MASK, b1h = __float_as_uint(fb[nt]) & TF32_MASK;
+                const uint32_t b0l = __float_as_uint(fa[nt] - __uint_as_float(b0h));
+                const uint32_t b1l = __float_as_uint(fb[nt] - __uint_as_float(b1h));
+                mma_tf32(acc[nt], alo[s], b0h, b1h);
+                mma_tf32(acc[nt], ahi[s], b0l, b1l);
+                mma_tf32(acc[nt], ahi[s], b0h, b1h);
+            }
+        }
+    }
+    // D fragment: acc[nt][0|1] -> kernel point g, channels c0 + (2t|2t+1)*NT + nt ; acc[nt][2|3] -> kernel point g+8
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int kp = g + 8 * r;
+        if (kp >= K) continue;
+        const size_t e0 = (size_t)n * ldk + (size_t)kp * cin + c0 + 2 * t * NT;
+        if (SPLIT) {
+            __align__(16) __nv_bfloat16 hi[2 * NT], lo[2 * NT];
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    const float v = acc[nt][2 * r + half];
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    hi[half * NT + nt] = h;
+                    lo[half * NT + nt] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+            if (NT >= 4) {
+#pragma unroll
+                for (int v = 0; v < (2 * NT) / 8; v++) {
+                    *reinterpret_cast<uint4*>(wf_hi + e0 + 8 * v) = *reinterpret_cast<const uint4*>(hi + 8 * v);
+                    *reinterpret_cast<uint4*>(wf_lo + e0 + 8 * v) = *reinterpret_cast<const uint4*>(lo + 8 * v);
+                }
+            } else if (NT == 2) {
+                *reinterpret_cast<uint2*>(wf_hi + e0) = *reinterpret_cast<const uint2*>(hi);
+                *reinterpret_cast<uint2*>(wf_lo + e0) = *reinterpret_cast<const uint2*>(lo);
+            } else {
+                *reinterpret_cast<uint32_t*>(wf_hi + e0) = *reinterpret_cast<const uint32_t*>(hi);
+                *reinterpret_cast<uint32_t*>(wf_lo + e0) = *reinterpret_cast<const uint32_t*>(lo);
+            }
+        } else {
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) wf[e0 + half * NT + nt] = acc[nt][2 * r + half];
+        }
+    }
+    if (blockIdx.y == 0) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        if (lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
+    }
+}
+
+static int g_agg_simt = 0;
+void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
+
 template <typename IdxT, bool SPLIT>
 static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, const IdxT* idx, int H, int idx_stride, const float* x,
                       int cin, int ldx, const uint8_t* rowflag, const float* kpts, int K, float inv_extent, float* wf,
@@ -131,6 +302,17 @@ static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, co
 {
     dim3 block(AGG_WARPS * 32);
     unsigned gx = (unsigned)cdiv64(nq, AGG_WARPS);
+    if (cin % 8 == 0 && ns > 0 && !g_agg_simt) {
+#define PCRCG_AGG_MMA(NT_) k_kpconv_aggregate_mma<IdxT, NT_, SPLIT><<<dim3(gx, (unsigned)(cin / (8 * NT_))), block, 0, st>>>( \
+        q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt)
+        if (cin % 64 == 0) PCRCG_AGG_MMA(8);
+        else if (cin % 32 == 0) PCRCG_AGG_MMA(4);
+        else if (cin % 16 == 0) PCRCG_AGG_MMA(2);
+        else PCRCG_AGG_MMA(1);
+#undef PCRCG_AGG_MMA
+        PCRCG_CUDA(cudaGetLastError());
+        return PCRCG_OK;
+    }
     if (cin <= 32) {
         k_kpconv_aggregate<IdxT, 1, SPLIT><<<dim3(gx, 1), block, 0, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
     } else if (cin <= 64) {
@@ -165,6 +347,7 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     PCRCG_REQUIRE(cin >= 1 && cout >= 1 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
     PCRCG_REQUIRE(nq < (1ll << 31) && ns < (1ll << 31), "kpconv: too many points");
     PCRCG_REQUIRE(kp_extent > 0.f, "kpconv: KP_extent must be positive");
+    PCRCG_REQUIRE((unsigned long long)ns * (unsigned long long)cin < (1ull << 32), "kpconv: feature table too large for 32-bit offsets");
     if (nq == 0) return PCRCG_OK;
     const int KC = K * cin;
     const bool tc = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC);

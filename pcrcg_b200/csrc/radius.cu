@@ -21,6 +21,7 @@ namespace pcrcg {
 
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr int RQ_WARPS = 8;
+constexpr int RQ_CAND = 384;         // candidate record indices staged per warp (longer candidate sets use the search path)
 constexpr int RQ_CAP = 256;          // matches kept in shared memory per warp; larger rows take the slow path
 
 // ---- bbox (same encoding as subsample.cu; kept local so both TUs stay self-contained) ------------
@@ -80,6 +81,11 @@ __device__ __forceinline__ int cell_coord(float x, float o, float cs)
     return (int)f;
 }
 
+__device__ __forceinline__ uint32_t cell_slot(uint64_t key, uint32_t cap)
+{
+    return __umulhi((uint32_t)(mix64(key) >> 32), cap);      // uniform in [0, cap)
+}
+
 __device__ __forceinline__ uint64_t cell_key(int cx, int cy, int cz)
 {
     return (uint64_t)(uint32_t)cx | ((uint64_t)(uint32_t)cy << 21) | ((uint64_t)(uint32_t)cz << 42);
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(256) k_cell_insert(const uint64_t* __restrict_
     int s0 = sstarts[c], len = sstarts[c + 1] - s0;
     uint32_t cap = 2u * (uint32_t)len + 1u, toff = 2u * (uint32_t)s0 + (uint32_t)c;
     uint64_t key = keys[i];
-    uint32_t h = (uint32_t)(mix64(key) % cap);
+    uint32_t h = cell_slot(key, cap);
     while (true) {
         uint32_t old = atomicCAS(&rep[toff + h], EMPTY, (uint32_t)i);
         if (old == EMPTY || keys[old] == key) break;
@@ -136,6 +142,52 @@ __device__ __forceinline__ float d2_ref(float qx, float qy, float qz, float4 p)
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Bitonic sort of R*32 64-bit keys held R per lane (element e = r*32 + lane), ascending, in registers.
+template <int R>
+__device__ __forceinline__ void warp_bitonic(unsigned long long (&v)[R], int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= R * 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((r & jr) == 0) {
+                        const bool asc = ((r * 32) & k) == 0;
+                        unsigned long long a = v[r], b = v[r | jr];
+                        unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+                        v[r] = asc ? lo : hi;
+                        v[r | jr] = asc ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool asc = (((r * 32) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    const unsigned long long mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                    v[r] = (lower == asc) ? mn : mx;
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void sort_and_write(const unsigned long long* buf, int nm, int lane, int32_t* row, int width, int ns)
+{
+    unsigned long long v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { int e = r * 32 + lane; v[r] = e < nm ? buf[e] : ~0ull; }
+    warp_bitonic<R>(v, lane);
+#pragma unroll
+    for (int r = 0; r < R; r++) { int e = r * 32 + lane; if (e < width) row[e] = e < nm ? (int32_t)(uint32_t)(v[r] & 0xffffffffull) : ns; }
+    for (int e = R * 32 + lane; e < width; e += 32) row[e] = ns;
+}
+
 // One warp per query.  rows == nullptr: count only.
 __global__ void __launch_bounds__(RQ_WARPS * 32) k_radius_query(
     const float* __restrict__ q, int nq, const int32_t* __restrict__ qstarts, const int32_t* __restrict__ sstarts, int nb,
@@ -146,6 +198,7 @@ __global__ void __launch_bounds__(RQ_WARPS * 32) k_radius_query(
     __shared__ unsigned long long s_buf[RQ_WARPS][RQ_CAP];
     __shared__ uint32_t s_pre[RQ_WARPS][28];
     __shared__ uint32_t s_st[RQ_WARPS][27];
+    __shared__ uint32_t s_cand[RQ_WARPS][RQ_CAND];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * RQ_WARPS + w;
     if (i >= nq) return;                      // warp-uniform
@@ -163,7 +216,7 @@ __global__ void __launch_bounds__(RQ_WARPS * 32) k_radius_query(
         if (cx >= 0 && cy >= 0 && cz >= 0) {
             uint64_t key = cell_key(cx, cy, cz);
             uint32_t cap = 2u * (uint32_t)slen + 1u, toff = 2u * (uint32_t)s0 + (uint32_t)c;
-            uint32_t h = (uint32_t)(mix64(key) % cap);
+            uint32_t h = cell_slot(key, cap);
             while (true) {
                 uint32_t r = rep[toff + h];
                 if (r == EMPTY) break;
@@ -185,24 +238,50 @@ __global__ void __launch_bounds__(RQ_WARPS * 32) k_radius_query(
     const uint32_t C = s_pre[w][27];
 
     int nm = 0;                                // matches so far (warp-uniform)
-    for (uint32_t base = 0; base < C; base += 32) {
-        uint32_t t = base + lane;
-        bool hit = false;
-        unsigned long long key = 0;
-        if (t < C) {
-            int lo = 0, hi = 27;               // find run: largest k with pre[k] <= t
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[w][mid] <= t) lo = mid; else hi = mid; }
-            float4 p = rec[s_st[w][lo] + (t - s_pre[w][lo])];
-            float d2 = d2_ref(qx, qy, qz, p);
-            hit = d2 < r2;
-            key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+    if (C <= (uint32_t)RQ_CAND) {
+        // expand the 27 runs into a flat list of record indices (each lane expands its own run)
+        if (lane < 27) {
+            const uint32_t p0 = s_pre[w][lane];
+            for (uint32_t t = 0; t < cnt; t++) s_cand[w][p0 + t] = st + t;
         }
-        uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            int pos = nm + __popc(bal & ((1u << lane) - 1u));
-            if (pos < RQ_CAP) buf[pos] = key;
+        __syncwarp();
+        for (uint32_t base = 0; base < C; base += 32) {
+            const uint32_t t = base + lane;
+            bool hit = false;
+            unsigned long long key = 0;
+            if (t < C) {
+                const float4 p = rec[s_cand[w][t]];
+                const float d2 = d2_ref(qx, qy, qz, p);
+                hit = d2 < r2;
+                key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = nm + __popc(bal & ((1u << lane) - 1u));
+                if (pos < RQ_CAP) buf[pos] = key;
+            }
+            nm += __popc(bal);
         }
-        nm += __popc(bal);
+    } else {
+        for (uint32_t base = 0; base < C; base += 32) {
+            uint32_t t = base + lane;
+            bool hit = false;
+            unsigned long long key = 0;
+            if (t < C) {
+                int lo = 0, hi = 27;               // find run: largest k with pre[k] <= t
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[w][mid] <= t) lo = mid; else hi = mid; }
+                float4 p = rec[s_st[w][lo] + (t - s_pre[w][lo])];
+                float d2 = d2_ref(qx, qy, qz, p);
+                hit = d2 < r2;
+                key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(p.w);
+            }
+            uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                int pos = nm + __popc(bal & ((1u << lane) - 1u));
+                if (pos < RQ_CAP) buf[pos] = key;
+            }
+            nm += __popc(bal);
+        }
     }
     if (lane == 0) {
         if (counts) counts[i] = nm;
@@ -212,7 +291,13 @@ __global__ void __launch_bounds__(RQ_WARPS * 32) k_radius_query(
     int32_t* row = rows + (size_t)i * row_stride;
     __syncwarp();
 
-    if (nm <= RQ_CAP) {
+    if (nm <= 32) {
+        sort_and_write<1>(buf, nm, lane, row, width, ns);
+    } else if (nm <= 64) {
+        sort_and_write<2>(buf, nm, lane, row, width, ns);
+    } else if (nm <= 128) {
+        sort_and_write<4>(buf, nm, lane, row, width, ns);
+    } else if (nm <= RQ_CAP) {
         int mp = 1;
         while (mp < nm) mp <<= 1;
         for (int k = nm + lane; k < mp; k += 32) buf[k] = ~0ull;

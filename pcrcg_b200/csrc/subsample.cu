@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_insert(const uint64_t* __restrict__ key
     uint32_t cap = 2u * (uint32_t)len + 1u;
     uint32_t toff = 2u * (uint32_t)s0 + (uint32_t)c;
     uint64_t key = keys[i];
-    uint32_t h = (uint32_t)(mix64(key) % cap);
+    uint32_t h = __umulhi((uint32_t)(mix64(key) >> 32), cap);
     while (true) {
         uint32_t old = atomicCAS(&rep[toff + h], EMPTY, (uint32_t)i);
         if (old == EMPTY || keys[old] == key) break;
