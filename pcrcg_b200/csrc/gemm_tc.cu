@@ -336,34 +336,49 @@ static int pool_setup()
 
 bool gemm_tc_shape_ok(int M, int N, int K) { return N % 16 == 0 && N >= 16 && K >= 16 && M >= 1; }
 
-// A already split: a_hi / a_lo bf16 [M, ldk] (ldk % 8 == 0).  B fp32, split here (weights are small).
-int gemm_tc_presplit_dev(const void* a_hi_v, const void* a_lo_v, int ldk, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M,
-                         int N, int K, const float* row_scale, cudaStream_t st)
+// Split (and transpose if needed) the fp32 B operand into bf16 hi/lo [N, ldk] (K contiguous).
+int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi_v, void* b_lo_v, cudaStream_t st)
 {
-    PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
-    PCRCG_TRY(get_encode());
-    PCRCG_TRY(pool_setup());
-    const __nv_bfloat16* a_hi = (const __nv_bfloat16*)a_hi_v;
-    const __nv_bfloat16* a_lo = (const __nv_bfloat16*)a_lo_v;
-    __nv_bfloat16 *b_hi = nullptr, *b_lo = nullptr;
-    const size_t b_elems = (size_t)N * ldk;
-    PCRCG_CUDA(cudaMallocAsync((void**)&b_hi, 2 * b_elems * sizeof(__nv_bfloat16) + 1024, st));
-    b_lo = b_hi + b_elems;
-    count_launches(2);
+    __nv_bfloat16* b_hi = (__nv_bfloat16*)b_hi_v;
+    __nv_bfloat16* b_lo = (__nv_bfloat16*)b_lo_v;
+    count_launches(1);
     if (b_is_nk) {
         long long tot = (long long)N * (ldk / 4);
         k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, ldk);
     } else {
         k_split_bf16_transpose<<<dim3((unsigned)cdiv64(ldk, 32), (unsigned)cdiv64(N, 32)), 256, 0, st>>>(B, ldb, K, N, b_hi, b_lo, ldk);
     }
-    int rc = PCRCG_OK;
-    if (cudaGetLastError() != cudaSuccess) { set_error("gemm_tc: split launch failed"); rc = PCRCG_ERR; }
-    if (rc == PCRCG_OK) {
-        if (N % 128 == 0) rc = launch_tc<128>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
-        else if (N % 64 == 0) rc = launch_tc<64>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
-        else if (N % 32 == 0) rc = launch_tc<32>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
-        else rc = launch_tc<16>(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
-    }
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+// Both operands already split: a_* bf16 [M, ldk], b_* bf16 [N, ldk] (ldk % 8 == 0).
+int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
+                     const float* row_scale, cudaStream_t st)
+{
+    PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
+    PCRCG_TRY(get_encode());
+    count_launches(1);
+    const __nv_bfloat16 *ah = (const __nv_bfloat16*)a_hi, *al = (const __nv_bfloat16*)a_lo, *bh = (const __nv_bfloat16*)b_hi,
+                        *bl = (const __nv_bfloat16*)b_lo;
+    if (N % 128 == 0) return launch_tc<128>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
+    if (N % 64 == 0) return launch_tc<64>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
+    if (N % 32 == 0) return launch_tc<32>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
+    return launch_tc<16>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
+}
+
+// A already split: a_hi / a_lo bf16 [M, ldk] (ldk % 8 == 0).  B fp32, split here (weights are small).
+int gemm_tc_presplit_dev(const void* a_hi_v, const void* a_lo_v, int ldk, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M,
+                         int N, int K, const float* row_scale, cudaStream_t st)
+{
+    PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
+    PCRCG_TRY(pool_setup());
+    __nv_bfloat16* b_hi = nullptr;
+    const size_t b_elems = (size_t)N * ldk;
+    PCRCG_CUDA(cudaMallocAsync((void**)&b_hi, 2 * b_elems * sizeof(__nv_bfloat16) + 1024, st));
+    __nv_bfloat16* b_lo = b_hi + b_elems;
+    int rc = gemm_tc_split_b_dev(B, ldb, b_is_nk, N, K, ldk, b_hi, b_lo, st);
+    if (rc == PCRCG_OK) rc = gemm_tc_core_dev(a_hi_v, a_lo_v, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st);
     cudaFreeAsync(b_hi, st);
     return rc;
 }

@@ -196,14 +196,28 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate_mma(
     for (int h0 = 0; h0 < H; h0 += MMA_KS * 8) {
         uint32_t ahi[MMA_KS][4], alo[MMA_KS][4];
         unsigned ja[MMA_KS], jb[MMA_KS];
+        bool vas[MMA_KS], vbs[MMA_KS];
+        // all index loads first (independent), then the flag loads of the counting lanes
 #pragma unroll
         for (int s = 0; s < MMA_KS; s++) {
             const int ha = h0 + 8 * s + t, hb = ha + 4;
             long long ia = ha < H ? (long long)row[ha] : (long long)ns;
             long long ib = hb < H ? (long long)row[hb] : (long long)ns;
-            const bool va = ia >= 0 && ia < ns, vb = ib >= 0 && ib < ns;
-            ja[s] = va ? (unsigned)ia : 0u;
-            jb[s] = vb ? (unsigned)ib : 0u;
+            vas[s] = ia >= 0 && ia < ns;
+            vbs[s] = ib >= 0 && ib < ns;
+            ja[s] = vas[s] ? (unsigned)ia : 0u;
+            jb[s] = vbs[s] ? (unsigned)ib : 0u;
+        }
+        if (g == 0 && blockIdx.y == 0) {
+            int fl[2 * MMA_KS];
+#pragma unroll
+            for (int s = 0; s < MMA_KS; s++) { fl[2 * s] = vas[s] ? (int)rowflag[ja[s]] : 0; fl[2 * s + 1] = vbs[s] ? (int)rowflag[jb[s]] : 0; }
+#pragma unroll
+            for (int s = 0; s < 2 * MMA_KS; s++) cnt += fl[s];
+        }
+#pragma unroll
+        for (int s = 0; s < MMA_KS; s++) {
+            const bool va = vas[s], vb = vbs[s];
             const float* spa = s_pts + 3 * (size_t)ja[s];
             const float* spb = s_pts + 3 * (size_t)jb[s];
             float w00 = (va && k0ok) ? influence(spa, k0x, k0y, k0z, inv_extent) : 0.f;
@@ -217,7 +231,6 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate_mma(
                 ahi[s][u] = hi;
                 alo[s][u] = __float_as_uint(wv[u] - __uint_as_float(hi));
             }
-            if (g == 0 && blockIdx.y == 0) cnt += (va ? (int)rowflag[ja[s]] : 0) + (vb ? (int)rowflag[jb[s]] : 0);
         }
 #pragma unroll
         for (int s = 0; s < MMA_KS; s++) {
@@ -292,6 +305,164 @@ __global__ void __launch_bounds__(AGG_WARPS * 32) k_kpconv_aggregate_mma(
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 64-channel-slab variant of the tensor-core aggregation (cin % 64 == 0: every production layer).
+// The neighbourhood of a point is first STAGED IN SHARED MEMORY with cp.async -- all (<= 40) feature
+// rows of the slab and the neighbour coordinates are requested back to back, so the warp pays one
+// memory round trip per point instead of one per k-step -- then the influence weights are computed
+// just in time per k-step (no weight fragments kept live) and fed to mma.sync with the feature
+// fragments read from shared memory (row stride 72 floats: conflict-free LDS.128 for the 4g / 32+4g
+// channel mapping).
+constexpr int A64_WARPS = 4;
+constexpr int A64_ROWS = 24;
+constexpr int A64_STRIDE = 72;
+constexpr int A64_SMEM = A64_WARPS * (A64_ROWS * A64_STRIDE + A64_ROWS * 4) * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem), "r"(sz) : "memory");
+}
+
+template <typename IdxT, bool SPLIT>
+__global__ void __launch_bounds__(A64_WARPS * 32) k_kpconv_aggregate_mma64(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const float* __restrict__ x, int cin, int ldx, const uint8_t* __restrict__ rowflag,
+    const float* __restrict__ kpts, int K, float inv_extent, float* __restrict__ wf, __nv_bfloat16* __restrict__ wf_hi,
+    __nv_bfloat16* __restrict__ wf_lo, int ldk, float* __restrict__ inv_cnt)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * A64_WARPS + w;
+    if (n >= nq) return;
+    float* s_feat = smem_f + (size_t)w * (A64_ROWS * A64_STRIDE + A64_ROWS * 4);
+    float* s_xyz = s_feat + A64_ROWS * A64_STRIDE;          // [row][x,y,z,valid]
+    const int g = lane >> 2, t = lane & 3;
+    const int c0 = blockIdx.y * 64;
+
+    const float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
+    const bool k1ok = g + 8 < K, k0ok = g < K;
+    const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
+    const float k0x = kpts[3 * ka] + qx, k0y = kpts[3 * ka + 1] + qy, k0z = kpts[3 * ka + 2] + qz;
+    const float k1x = kpts[3 * kb] + qx, k1y = kpts[3 * kb + 1] + qy, k1z = kpts[3 * kb + 2] + qz;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    int cnt = 0;
+    const IdxT* row = idx + (size_t)n * idx_stride;
+    const float* xl = x + c0 + (lane & 15) * 4;             // 16-byte chunk of the slab copied by this lane
+
+    for (int h0 = 0; h0 < H; h0 += A64_ROWS) {
+        // ---- stage: indices (coalesced), coordinates, flags, feature rows ----
+        int ja = ns, jb = ns;
+        if (lane < A64_ROWS && h0 + lane < H) { long long v = (long long)row[h0 + lane]; ja = (v >= 0 && v < ns) ? (int)v : ns; }
+        if (lane < A64_ROWS - 32 && h0 + 32 + lane < H) { long long v = (long long)row[h0 + 32 + lane]; jb = (v >= 0 && v < ns) ? (int)v : ns; }
+        const bool va = ja < ns, vb = jb < ns;
+        if (lane < A64_ROWS) {
+            float* d = s_xyz + lane * 4;
+            const float* sp = s_pts + 3 * (size_t)(va ? ja : 0);
+            cp_async4(d, sp, va); cp_async4(d + 1, sp + 1, va); cp_async4(d + 2, sp + 2, va);
+            d[3] = va ? 1.f : 0.f;
+            if (lane < A64_ROWS - 32) {
+                float* d2 = s_xyz + (32 + lane) * 4;
+                const float* sp2 = s_pts + 3 * (size_t)(vb ? jb : 0);
+                cp_async4(d2, sp2, vb); cp_async4(d2 + 1, sp2 + 1, vb); cp_async4(d2 + 2, sp2 + 2, vb);
+                d2[3] = vb ? 1.f : 0.f;
+            }
+        }
+#pragma unroll 4
+        for (int r = 0; r < A64_ROWS; r += 2) {
+            const int rr = r + (lane >> 4);
+            const int src_lane = rr & 31;
+            const int j_lo = __shfl_sync(0xffffffffu, ja, src_lane), j_hi = __shfl_sync(0xffffffffu, jb, src_lane);
+            const int j = rr < 32 ? j_lo : j_hi;
+            const bool v = j < ns;
+            cp_async16(s_feat + rr * A64_STRIDE + (lane & 15) * 4, xl + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldx), v);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (blockIdx.y == 0) {
+            const bool fa = va && rowflag[ja] != 0, fb = vb && rowflag[jb] != 0;
+            cnt += __popc(__ballot_sync(0xffffffffu, fa)) + __popc(__ballot_sync(0xffffffffu, fb));
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+
+        // ---- compute: one k-step = 8 neighbours ----
+#pragma unroll
+        for (int s = 0; s < A64_ROWS / 8; s++) {
+            if (h0 + 8 * s >= H) break;                    // warp-uniform
+            const float4 pa = *reinterpret_cast<const float4*>(s_xyz + (8 * s + t) * 4);
+            const float4 pb = *reinterpret_cast<const float4*>(s_xyz + (8 * s + t + 4) * 4);
+            float wv[4];
+            {
+                const float sa[3] = { pa.x, pa.y, pa.z }, sb[3] = { pb.x, pb.y, pb.z };
+                wv[0] = (pa.w != 0.f && k0ok) ? influence(sa, k0x, k0y, k0z, inv_extent) : 0.f;
+                wv[1] = (pa.w != 0.f && k1ok) ? influence(sa, k1x, k1y, k1z, inv_extent) : 0.f;
+                wv[2] = (pb.w != 0.f && k0ok) ? influence(sb, k0x, k0y, k0z, inv_extent) : 0.f;
+                wv[3] = (pb.w != 0.f && k1ok) ? influence(sb, k1x, k1y, k1z, inv_extent) : 0.f;
+            }
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ahi[u] = __float_as_uint(wv[u]) & TF32_MASK;
+                alo[u] = __float_as_uint(wv[u] - __uint_as_float(ahi[u]));
+            }
+            const float* ra = s_feat + (8 * s + t) * A64_STRIDE + 4 * g;
+            const float* rb = s_feat + (8 * s + t + 4) * A64_STRIDE + 4 * g;
+            const float4 A0 = *reinterpret_cast<const float4*>(ra), A1 = *reinterpret_cast<const float4*>(ra + 32);
+            const float4 B0 = *reinterpret_cast<const float4*>(rb), B1 = *reinterpret_cast<const float4*>(rb + 32);
+            const float fa[8] = { A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w };
+            const float fb[8] = { B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w };
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const uint32_t b0h = __float_as_uint(fa[nt]) & TF32_MASK, b1h = __float_as_uint(fb[nt]) & TF32_MASK;
+                const uint32_t b0l = __float_as_uint(fa[nt] - __uint_as_float(b0h));
+                const uint32_t b1l = __float_as_uint(fb[nt] - __uint_as_float(b1h));
+                mma_tf32(acc[nt], alo, b0h, b1h);
+                mma_tf32(acc[nt], ahi, b0l, b1l);
+                mma_tf32(acc[nt], ahi, b0h, b1h);
+            }
+        }
+        __syncwarp();
+    }
+    // tile nt < 4: column j <-> channel 4j + nt ; nt >= 4: channel 32 + 4j + (nt-4).  Lane holds columns 2t, 2t+1:
+    // channels [8t, 8t+8) and [32+8t, 32+8t+8) for kernel points g (acc[.][0|1]) and g+8 (acc[.][2|3]).
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int kp = g + 8 * r;
+        if (kp >= K) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {                     // hf = 0: channels 8t.. ; 1: 32+8t..
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = acc[hf * 4 + (c & 3)][2 * r + (c >> 2)];
+            const size_t e0 = (size_t)n * ldk + (size_t)kp * cin + c0 + hf * 32 + 8 * t;
+            if (SPLIT) {
+                __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    hi[c] = __float2bfloat16_rn(v[c]);
+                    lo[c] = __float2bfloat16_rn(v[c] - __bfloat162float(hi[c]));
+                }
+                *reinterpret_cast<uint4*>(wf_hi + e0) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(wf_lo + e0) = *reinterpret_cast<const uint4*>(lo);
+            } else {
+                *reinterpret_cast<float4*>(wf + e0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(wf + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+    if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
+}
+
 static int g_agg_simt = 0;
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
 
@@ -305,7 +476,15 @@ static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, co
     if (cin % 8 == 0 && ns > 0 && !g_agg_simt) {
 #define PCRCG_AGG_MMA(NT_) k_kpconv_aggregate_mma<IdxT, NT_, SPLIT><<<dim3(gx, (unsigned)(cin / (8 * NT_))), block, 0, st>>>( \
         q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt)
-        if (cin % 64 == 0) PCRCG_AGG_MMA(8);
+        if (cin % 64 == 0) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                PCRCG_CUDA(cudaFuncSetAttribute(k_kpconv_aggregate_mma64<IdxT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM));
+                attr_done = true;
+            }
+            k_kpconv_aggregate_mma64<IdxT, SPLIT><<<dim3((unsigned)cdiv64(nq, A64_WARPS), (unsigned)(cin / 64)), A64_WARPS * 32, A64_SMEM, st>>>(
+                q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
+        }
         else if (cin % 32 == 0) PCRCG_AGG_MMA(4);
         else if (cin % 16 == 0) PCRCG_AGG_MMA(2);
         else PCRCG_AGG_MMA(1);
@@ -332,10 +511,30 @@ int gemm_tc_presplit_dev(const void* a_hi, const void* a_lo, int ldk, const floa
                          int K, const float* row_scale, cudaStream_t st);
 int gemm_force_simt_get();
 
+int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi, void* b_lo, cudaStream_t st);
+int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
+                     const float* row_scale, cudaStream_t st);
+
+// The [Nq, K*cin] aggregate is produced and consumed in chunks of query points through two
+// alternating buffers of at most WF_CHUNK_BYTES each, which bounds the workspace for very large
+// batches.  (Measured on B200: L2-sized 40 MB chunks -- meant to keep the intermediate out of HBM --
+// LOSE 25 %: a chunk is then < 148 contraction tiles and both kernels run under-filled; see DESIGN.md.)
+constexpr size_t WF_CHUNK_BYTES = 4ull << 30;
+
+static int64_t kpconv_chunk_rows(int64_t nq, size_t ldk)
+{
+    int64_t rows = (int64_t)(WF_CHUNK_BYTES / (ldk * sizeof(float)));
+    rows = rows / 128 * 128;
+    if (rows < 1024) rows = 1024;
+    return rows < nq ? rows : (nq > 0 ? nq : 1);
+}
+
 size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 {
     size_t ldk = ((size_t)K * cin + 7) / 8 * 8;
-    return align_up((size_t)nq * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) + 1024;
+    size_t chunk = (size_t)kpconv_chunk_rows(nq, ldk);
+    return 2 * align_up(chunk * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) +
+           align_up((size_t)2048 * ldk * sizeof(float), 256) + 2048;      // + split weights for cout <= 2048
 }
 
 // weights: [K, cin, cout] row-major (the reference's Parameter layout)
@@ -344,43 +543,63 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
                        const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     PCRCG_REQUIRE(K >= 1 && K <= KP_MAX - 1, "kpconv: kernel_size must be in [1,15]");
-    PCRCG_REQUIRE(cin >= 1 && cout >= 1 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
+    PCRCG_REQUIRE(cin >= 1 && cout >= 1 && cout <= 2048 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
     PCRCG_REQUIRE(nq < (1ll << 31) && ns < (1ll << 31), "kpconv: too many points");
     PCRCG_REQUIRE(kp_extent > 0.f, "kpconv: KP_extent must be positive");
     PCRCG_REQUIRE((unsigned long long)ns * (unsigned long long)cin < (1ull << 32), "kpconv: feature table too large for 32-bit offsets");
     if (nq == 0) return PCRCG_OK;
     const int KC = K * cin;
     const bool tc = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC);
-    const int ldk = tc ? (KC + 7) / 8 * 8 : KC;
+    const int ldk = (KC + 7) / 8 * 8;
+    const int64_t chunk = kpconv_chunk_rows(nq, (size_t)ldk);
     Workspace W(ws, ws_bytes);
-    float* wf = W.take<float>((size_t)nq * ldk);
+    float* wf_buf[2] = { W.take<float>((size_t)chunk * ldk), W.take<float>((size_t)chunk * ldk) };
     float* inv_cnt = W.take<float>((size_t)nq);
     uint8_t* rowflag = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
+    __nv_bfloat16* b_hi = (__nv_bfloat16*)W.take<float>((size_t)cout * ldk);
+    __nv_bfloat16* b_lo = b_hi + (size_t)cout * ldk;
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
-    __nv_bfloat16* wf_hi = (__nv_bfloat16*)wf;
-    __nv_bfloat16* wf_lo = wf_hi + (size_t)nq * ldk;
     const float inv_extent = 1.0f / kp_extent;
     {
-        ProfScope prof(PC_KPCONV_AGG, st, 2);
+        ProfScope prof(PC_KPCONV_AGG, st, 1);
         if (ns > 0) {
             k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag);
             PCRCG_CUDA(cudaGetLastError());
         }
-        int rc;
-        if (idx_is_i64) {
-            rc = tc ? launch_agg<long long, true>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt, st)
-                    : launch_agg<long long, false>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt, st);
-        } else {
-            rc = tc ? launch_agg<int, true>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt, st)
-                    : launch_agg<int, false>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt, st);
-        }
-        if (rc) return rc;
     }
     if (tc) {
-        ProfScope prof(PC_GEMM, st, 1);
-        return gemm_tc_presplit_dev(wf_hi, wf_lo, ldk, weights, cout, 0, out, cout, (int)nq, cout, KC, inv_cnt, st);
+        ProfScope prof(PC_GEMM, st, 0);
+        PCRCG_TRY(gemm_tc_split_b_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, st));
     }
-    return gemm_dev(wf, KC, weights, cout, 0, out, cout, (int)nq, cout, KC, inv_cnt, st);
+    const size_t idx_bytes = idx_is_i64 ? 8 : 4;
+    int it = 0;
+    for (int64_t r0 = 0; r0 < nq; r0 += chunk, it++) {
+        const int rows = (int)((nq - r0) < chunk ? (nq - r0) : chunk);
+        float* wf = wf_buf[it & 1];
+        __nv_bfloat16* wf_hi = (__nv_bfloat16*)wf;
+        __nv_bfloat16* wf_lo = wf_hi + (size_t)rows * ldk;
+        const float* qp = q_pts + 3 * (size_t)r0;
+        const void* ip = (const char*)idx + (size_t)r0 * idx_stride * idx_bytes;
+        {
+            ProfScope prof(PC_KPCONV_AGG, st, 1);
+            int rc;
+            if (idx_is_i64) {
+                rc = tc ? launch_agg<long long, true>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt + r0, st)
+                        : launch_agg<long long, false>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt + r0, st);
+            } else {
+                rc = tc ? launch_agg<int, true>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt + r0, st)
+                        : launch_agg<int, false>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt + r0, st);
+            }
+            if (rc) return rc;
+        }
+        if (tc) {
+            ProfScope prof(PC_GEMM, st, 0);
+            PCRCG_TRY(gemm_tc_core_dev(wf_hi, wf_lo, b_hi, b_lo, ldk, out + (size_t)r0 * cout, cout, rows, cout, KC, inv_cnt + r0, st));
+        } else {
+            PCRCG_TRY(gemm_dev(wf, ldk, weights, cout, 0, out + (size_t)r0 * cout, cout, rows, cout, KC, inv_cnt + r0, st));
+        }
+    }
+    return PCRCG_OK;
 }
 
 }  // namespace pcrcg
