@@ -90,6 +90,13 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
  * [N,K] (b_is_nk = 1, nn.Linear.weight of models/blocks.py:490).  Row-major, leading dims in elements. */
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc,
                    int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
+/* The tensor-core contraction with operands already split into bf16 (hi, lo) planes
+ * (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)):  a_* [M,ldk], b_* [N,ldk], K contiguous, ldk % 8 == 0,
+ * N % 16 == 0.  pcrcg_split_bf16_dev produces such planes from fp32 rows. */
+int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols, void* hi, void* lo, int32_t ldo,
+                         pcrcg_stream_t stream);
+int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C,
+                          int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
 /* 1: force the fp32 CUDA-core contraction (parity anchor); 0: tcgen05 tensor-core path where shapes allow. */
 void pcrcg_gemm_force_simt(int32_t on);
 
@@ -99,12 +106,14 @@ void pcrcg_gemm_force_simt(int32_t on);
  * seg_starts [nseg+1] int32 device.  mean / rstd [nseg,C].
  *   out = act( (x-mean)*rstd + shortcut' ),  shortcut' = (sc-sc_mean)*sc_rstd | sc | 0,
  *   act = LeakyReLU(slope) when slope >= 0, identity when slope < 0;  mean == NULL skips the normalisation.
+ * split_hi / split_lo (bf16 [n, split_ld], may be NULL): the result is ALSO emitted as the (hi, lo) planes the
+ * next tensor-core contraction consumes, saving that contraction's own split pass.
  * ------------------------------------------------------------------------------------------- */
 int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps,
                        float* mean, float* rstd, pcrcg_stream_t stream);
 int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
                        const float* rstd, const float* sc, const float* sc_mean, const float* sc_rstd, float slope,
-                       float* out, pcrcg_stream_t stream);
+                       float* out, void* split_hi, void* split_lo, int32_t split_ld, pcrcg_stream_t stream);
 
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,

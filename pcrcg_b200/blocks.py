@@ -83,9 +83,9 @@ class BatchNormBlock(nn.Module):
         if not use_bn:
             self.bias = Parameter(torch.zeros(in_dim, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, x, segments=None, slope=None):
+    def forward(self, x, segments=None, slope=None, emit_split=False):
         if self.use_bn:
-            return ops.instance_norm_act(x, segments, slope)
+            return ops.instance_norm_act(x, segments, slope, emit_split=emit_split)
         x = x + self.bias
         return x if slope is None else torch.nn.functional.leaky_relu(x, slope)
 
@@ -146,7 +146,7 @@ class SimpleBlock(nn.Module):
     def forward(self, x, batch):
         q_pts, s_pts, inds, out_layer = _block_geometry(self.block_name, self.layer_ind, batch)
         x = self.KPConv(q_pts, s_pts, inds, x)
-        return self.batch_norm(x, _segments(batch, out_layer), 0.1)
+        return self.batch_norm(x, _segments(batch, out_layer), 0.1, emit_split=True)      # feeds the next block's unary1
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -170,16 +170,16 @@ class ResnetBottleneckBlock(nn.Module):
         seg_in, seg_out = _segments(batch, self.layer_ind), _segments(batch, out_layer)
         x = self.unary1(features, segments=seg_in) if isinstance(self.unary1, UnaryBlock) else features
         x = self.KPConv(q_pts, s_pts, inds, x)
-        x = self.batch_norm_conv(x, seg_out, 0.1)
+        x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True)                  # feeds unary2
         y = self.unary2.mlp(x)                                       # raw Linear; its norm is fused below
         shortcut = ops.max_pool(features, inds) if "strided" in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):
             sc_raw = self.unary_shortcut.mlp(shortcut)
             if self.use_bn:
-                return ops.instance_norm_act(y, seg_out, 0.1, shortcut=sc_raw, shortcut_norm=True)
+                return ops.instance_norm_act(y, seg_out, 0.1, shortcut=sc_raw, shortcut_norm=True, emit_split=True)
             return ops.add_act(y + self.unary2.batch_norm.bias, sc_raw + self.unary_shortcut.batch_norm.bias, 0.1)
         if self.use_bn:
-            return ops.instance_norm_act(y, seg_out, 0.1, shortcut=shortcut, shortcut_norm=False)
+            return ops.instance_norm_act(y, seg_out, 0.1, shortcut=shortcut, shortcut_norm=False, emit_split=True)
         return ops.add_act(y + self.unary2.batch_norm.bias, shortcut, 0.1)
 
 

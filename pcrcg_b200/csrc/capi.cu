@@ -57,9 +57,11 @@ int kpconv_forward_dev(const float*, int64_t, const float*, int64_t, const void*
                        int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t);
 int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
 void gemm_set_force_simt(int);
+int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
+int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
 int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
-                 const float*, float, float*, cudaStream_t);
+                 const float*, float, float*, void*, void*, int32_t, cudaStream_t);
 int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
@@ -219,6 +221,18 @@ int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int
 
 void pcrcg_gemm_force_simt(int32_t on) { gemm_set_force_simt(on); }
 
+int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols, void* hi, void* lo, int32_t ldo, pcrcg_stream_t stream)
+{
+    return split_bf16_dev(x, ldx, rows, cols, hi, lo, ldo, (cudaStream_t)stream);
+}
+
+int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C, int32_t ldc,
+                          int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream)
+{
+    ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
+    return gemm_tc_core_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
+}
+
 int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,
                        pcrcg_stream_t stream)
 {
@@ -226,9 +240,11 @@ int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
 }
 
 int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
-                       const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, pcrcg_stream_t stream)
+                       const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
+                       int32_t split_ld, pcrcg_stream_t stream)
 {
-    return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, (cudaStream_t)stream);
+    return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld,
+                        (cudaStream_t)stream);
 }
 
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H, int32_t idx_stride,

@@ -8,6 +8,8 @@
 // (the reference processes one pair per batch, i.e. one segment).
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace pcrcg {
 
 // ---- column statistics: mean / rstd per (segment, column) ----------------------------------------
@@ -72,13 +74,15 @@ __global__ void __launch_bounds__(256) k_norm_act(const float* __restrict__ x, i
                                                   const int32_t* __restrict__ seg_starts, int nseg, const float* __restrict__ mean,
                                                   const float* __restrict__ rstd, const float* __restrict__ sc, int ldsc,
                                                   const float* __restrict__ sc_mean, const float* __restrict__ sc_rstd, float slope,
-                                                  float* __restrict__ out, int ldo)
+                                                  float* __restrict__ out, int ldo, __nv_bfloat16* __restrict__ hi,
+                                                  __nv_bfloat16* __restrict__ lo, int lds)
 {
     const int c4 = (C + 3) >> 2;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)n * c4) return;
     const int r = (int)(e / c4), cb = (int)(e - (long long)r * c4) * 4;
     const int seg = nseg > 1 ? cloud_of(seg_starts, nseg, r) : 0;
+    float vv[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
     for (int u = 0; u < 4; u++) {
         int c = cb + u;
@@ -92,6 +96,17 @@ __global__ void __launch_bounds__(256) k_norm_act(const float* __restrict__ x, i
         }
         if (slope >= 0.f) v = v > 0.f ? v : v * slope;
         out[(size_t)r * ldo + c] = v;
+        vv[u] = v;
+    }
+    if (hi != nullptr) {          // bf16 (hi, lo) planes of the result for the next tensor-core contraction (lds % 8 == 0)
+        __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            h[u] = __float2bfloat16_rn(vv[u]);
+            l[u] = __float2bfloat16_rn(vv[u] - __bfloat162float(h[u]));
+        }
+        *reinterpret_cast<uint2*>(hi + (size_t)r * lds + cb) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + (size_t)r * lds + cb) = *reinterpret_cast<const uint2*>(l);
     }
 }
 
@@ -148,13 +163,15 @@ int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
 }
 
 int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
-                 const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, cudaStream_t st)
+                 const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
+                 int32_t split_ld, cudaStream_t st)
 {
     if (n == 0) return PCRCG_OK;
+    PCRCG_REQUIRE(split_hi == nullptr || (split_lo != nullptr && split_ld % 8 == 0 && split_ld >= C), "norm_act: bad split geometry");
     ProfScope prof(PC_NORM, st, 1);
     long long tot = (long long)n * ((C + 3) / 4);
     k_norm_act<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, mean, rstd, sc, C, sc_mean, sc_rstd, slope,
-                                                          out, C);
+                                                          out, C, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, split_ld);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

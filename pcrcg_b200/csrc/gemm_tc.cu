@@ -336,6 +336,17 @@ static int pool_setup()
 
 bool gemm_tc_shape_ok(int M, int N, int K) { return N % 16 == 0 && N >= 16 && K >= 16 && M >= 1; }
 
+int split_bf16_dev(const float* x, int ldx, int64_t rows, int cols, void* hi, void* lo, int ldo, cudaStream_t st)
+{
+    PCRCG_REQUIRE(ldo % 8 == 0 && ldo >= cols && rows >= 0, "split_bf16: bad geometry");
+    if (rows == 0) return PCRCG_OK;
+    count_launches(1);
+    long long tot = (long long)rows * (ldo / 4);
+    k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, ldx, (int)rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldo);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
 // Split (and transpose if needed) the fp32 B operand into bf16 hi/lo [N, ldk] (K contiguous).
 int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi_v, void* b_lo_v, cudaStream_t st)
 {

@@ -124,15 +124,34 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
     return out
 
 
+_force_simt = False
+
+
+def _split_planes(n, c, device):
+    ld = (c + 7) // 8 * 8
+    return (torch.empty((n, ld), dtype=torch.bfloat16, device=device), torch.empty((n, ld), dtype=torch.bfloat16, device=device), ld)
+
+
 def linear(x, weight):
-    """nn.Linear(bias=False): x [N,Cin] @ weight[Cout,Cin]^T   (models/blocks.py:490,497)"""
+    """nn.Linear(bias=False): x [N,Cin] @ weight[Cout,Cin]^T   (models/blocks.py:490,497).
+    If the producer of ``x`` attached its bf16 (hi, lo) planes (``x._pcrcg_split``) the tensor-core
+    contraction consumes them directly."""
     _need_cuda(x, weight)
     x, weight = _f32c(x), _f32c(weight)
     n, cin = x.shape
     cout = weight.shape[0]
     out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    L = lib()
+    sp = getattr(x, "_pcrcg_split", None)
     with torch.cuda.device(x.device):
-        check(lib().pcrcg_gemm_dev(x.data_ptr(), cin, weight.data_ptr(), cin, 1, out.data_ptr(), cout, n, cout, cin, None, _stream()))
+        if sp is not None and not _force_simt and cout % 16 == 0 and cin >= 16 and n >= 1:
+            hi, lo, ld = sp
+            bh, bl, _ = _split_planes(cout, cin, x.device)
+            check(L.pcrcg_split_bf16_dev(weight.data_ptr(), cin, cout, cin, bh.data_ptr(), bl.data_ptr(), ld, _stream()))
+            check(L.pcrcg_gemm_bf16x3_dev(hi.data_ptr(), lo.data_ptr(), bh.data_ptr(), bl.data_ptr(), ld, out.data_ptr(), cout, n, cout, cin,
+                                          None, _stream()))
+        else:
+            check(L.pcrcg_gemm_dev(x.data_ptr(), cin, weight.data_ptr(), cin, 1, out.data_ptr(), cout, n, cout, cin, None, _stream()))
     return out
 
 
@@ -166,9 +185,10 @@ def column_stats(x, segments=None, eps=1e-5):
     return mean, rstd, seg
 
 
-def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5):
+def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5, emit_split=False):
     """act(IN(x) + [IN](shortcut)) with act = LeakyReLU(slope) or identity (slope=None).
-    models/blocks.py:456-463 (+ :501, :590, :662, :678)."""
+    models/blocks.py:456-463 (+ :501, :590, :662, :678).  emit_split: also write the bf16 (hi, lo)
+    planes of the result (attached as ``out._pcrcg_split``) for a following :func:`linear`."""
     _need_cuda(x, shortcut)
     x = _f32c(x)
     n, c = x.shape
@@ -180,9 +200,13 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
             scm, scr, _ = column_stats(shortcut, segments, eps)
     out = torch.empty_like(x)
     p = lambda t: t.data_ptr() if t is not None else None
+    sp = _split_planes(n, c, x.device) if (emit_split and c % 8 == 0 and not _force_simt) else None
     with torch.cuda.device(x.device):
         check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
-                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), out.data_ptr(), _stream()))
+                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), out.data_ptr(),
+                                       sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0, _stream()))
+    if sp is not None:
+        out._pcrcg_split = sp
     return out
 
 
@@ -194,7 +218,7 @@ def add_act(x, shortcut, slope):
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), 1, None, None, shortcut.data_ptr(), None, None,
-                                       float(slope), out.data_ptr(), _stream()))
+                                       float(slope), out.data_ptr(), None, None, 0, _stream()))
     return out
 
 
@@ -224,4 +248,6 @@ def closest_pool(x, inds):
 
 def force_simt_contraction(on):
     """True: fp32 CUDA-core contraction (parity anchor); False: tcgen05 tensor cores where shapes allow."""
+    global _force_simt
+    _force_simt = bool(on)
     lib().pcrcg_gemm_force_simt(1 if on else 0)
