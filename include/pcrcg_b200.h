@@ -99,6 +99,9 @@ int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, 
                           int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
 /* 1: force the fp32 CUDA-core contraction (parity anchor); 0: tcgen05 tensor-core path where shapes allow. */
 void pcrcg_gemm_force_simt(int32_t on);
+/* A/B switches for measurements: "contraction_simt", "aggregate_simt" (CUDA-core variants of the two KPConv stages),
+ * "norm_vectorised" (float4 InstanceNorm apply kernel, default 1). */
+int pcrcg_set_option(const char* name, int32_t value);
 
 /* ---------------------------------------------------------------------------------------------
  * InstanceNorm over the rows of each segment (= fragment pair) -- models/blocks.py:448,456-463 --

@@ -39,6 +39,7 @@ SIGNATURES = {
     "pcrcg_gemm_dev": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "pcrcg_split_bf16_dev": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _I32, _P]),
     "pcrcg_gemm_bf16x3_dev": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "pcrcg_set_option": (C.c_int, [C.c_char_p, _I32]),
     "pcrcg_gemm_force_simt": (None, [_I32]),
     "pcrcg_colstats_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _F, _P, _P, _P]),
     "pcrcg_norm_act_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I32, _P]),

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
 
@@ -57,6 +58,8 @@ int kpconv_forward_dev(const float*, int64_t, const float*, int64_t, const void*
                        int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t);
 int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
 void gemm_set_force_simt(int);
+void dense_set_norm_v4(int);
+void kpconv_set_agg_simt(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
@@ -220,6 +223,15 @@ int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int
 }
 
 void pcrcg_gemm_force_simt(int32_t on) { gemm_set_force_simt(on); }
+
+int pcrcg_set_option(const char* name, int32_t value)
+{
+    if (!strcmp(name, "contraction_simt")) gemm_set_force_simt(value);
+    else if (!strcmp(name, "aggregate_simt")) kpconv_set_agg_simt(value);
+    else if (!strcmp(name, "norm_vectorised")) dense_set_norm_v4(value);
+    else { set_error("pcrcg_set_option: unknown option '%s'", name); return PCRCG_ERR; }
+    return PCRCG_OK;
+}
 
 int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols, void* hi, void* lo, int32_t ldo, pcrcg_stream_t stream)
 {

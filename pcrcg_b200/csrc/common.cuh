@@ -71,6 +71,9 @@ struct Workspace {
     bool ok() const { return dry || off <= size; }
 };
 
+// Keeps the stream-ordered allocator's memory cached (release threshold = max) -- call before cudaMallocAsync.
+int pool_setup();
+
 // ---- primitives (scan_sort.cu) -----------------------------------------------------------------
 // out[i] = sum_{j<i} in[j] for i in [0,n]; out has n+1 entries (out[n] = total).  in may alias out.
 size_t scan_ws_bytes(int64_t n);

@@ -110,6 +110,80 @@ __global__ void __launch_bounds__(256) k_norm_act(const float* __restrict__ x, i
     }
 }
 
+// Vectorised variant (C % 4 == 0): a thread owns one 4-channel group (mean / rstd in registers) and
+// NA_UNROLL rows whose float4 loads are all issued before the arithmetic; a block covers
+// (256 / column groups) * NA_UNROLL consecutive rows and re-reads the statistics if it crosses a segment.
+constexpr int NA_UNROLL = 4;
+
+__device__ __forceinline__ float4 na_apply(float4 v, float4 mu, float4 rs)
+{
+    return make_float4((v.x - mu.x) * rs.x, (v.y - mu.y) * rs.y, (v.z - mu.z) * rs.z, (v.w - mu.w) * rs.w);
+}
+
+__global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x, int n, int C, const int32_t* __restrict__ seg_starts,
+                                                     int nseg, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ sc, const float* __restrict__ sc_mean,
+                                                     const float* __restrict__ sc_rstd, float slope, float* __restrict__ out,
+                                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int lds,
+                                                     int tcols, int trows)
+{
+    const int c4 = C >> 2;
+    const int tx = threadIdx.x % tcols, ty = threadIdx.x / tcols;
+    if (ty >= trows) return;
+    const int R0 = blockIdx.x * (trows * NA_UNROLL);
+    for (int cg = tx; cg < c4; cg += tcols) {
+        float4 v[NA_UNROLL], s[NA_UNROLL];
+        int rr[NA_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NA_UNROLL; u++) {
+            rr[u] = R0 + ty + u * trows;
+            if (rr[u] < n) {
+                v[u] = *reinterpret_cast<const float4*>(x + (size_t)rr[u] * C + 4 * cg);
+                if (sc) s[u] = *reinterpret_cast<const float4*>(sc + (size_t)rr[u] * C + 4 * cg);
+            }
+        }
+        int seg = -1;
+        float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f), smu = mu, srs = rs;
+#pragma unroll
+        for (int u = 0; u < NA_UNROLL; u++) {
+            const int r = rr[u];
+            if (r >= n) break;
+            if (seg < 0 || r >= seg_starts[seg + 1]) {
+                seg = nseg > 1 ? cloud_of(seg_starts, nseg, r) : 0;
+                if (mean) {
+                    mu = *reinterpret_cast<const float4*>(mean + (size_t)seg * C + 4 * cg);
+                    rs = *reinterpret_cast<const float4*>(rstd + (size_t)seg * C + 4 * cg);
+                }
+                if (sc_mean) {
+                    smu = *reinterpret_cast<const float4*>(sc_mean + (size_t)seg * C + 4 * cg);
+                    srs = *reinterpret_cast<const float4*>(sc_rstd + (size_t)seg * C + 4 * cg);
+                }
+            }
+            float4 o = na_apply(v[u], mu, rs);
+            if (sc) {
+                const float4 t = na_apply(s[u], smu, srs);
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            if (slope >= 0.f) {
+                o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+                o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+            }
+            *reinterpret_cast<float4*>(out + (size_t)r * C + 4 * cg) = o;
+            if (hi != nullptr) {
+                const float vv[4] = { o.x, o.y, o.z, o.w };
+                __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    h[k] = __float2bfloat16_rn(vv[k]);
+                    l[k] = __float2bfloat16_rn(vv[k] - __bfloat162float(h[k]));
+                }
+                *reinterpret_cast<uint2*>(hi + (size_t)r * lds + 4 * cg) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(lo + (size_t)r * lds + 4 * cg) = *reinterpret_cast<const uint2*>(l);
+            }
+        }
+    }
+}
+
 // ---- gathers --------------------------------------------------------------------------------------
 // max over the listed rows; a shadow index contributes the zero row (models/blocks.py:95-101)
 template <typename IdxT>
@@ -144,11 +218,15 @@ __global__ void __launch_bounds__(256) k_closest_pool(const float* __restrict__ 
     for (int c = lane; c < C; c += 32) out[(size_t)n * C + c] = ok ? __ldg(x + (size_t)j * ldx + c) : 0.f;
 }
 
+static int g_norm_v4 = 1;
+void dense_set_norm_v4(int v) { g_norm_v4 = v; }
+
 // ---- host side ---------------------------------------------------------------------------------
 int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,
                  cudaStream_t st)
 {
     PCRCG_REQUIRE(C >= 1 && nseg >= 1 && nseg < 65536 && n < (1ll << 31), "instance norm: bad dimensions");
+    PCRCG_TRY(pool_setup());
     ProfScope prof(PC_NORM, st, 2);
     double* acc = nullptr;
     const size_t acc_bytes = (size_t)nseg * 2 * C * sizeof(double);
@@ -169,6 +247,15 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
     if (n == 0) return PCRCG_OK;
     PCRCG_REQUIRE(split_hi == nullptr || (split_lo != nullptr && split_ld % 8 == 0 && split_ld >= C), "norm_act: bad split geometry");
     ProfScope prof(PC_NORM, st, 1);
+    if (C % 4 == 0 && n < (1ll << 31) && g_norm_v4) {
+        const int c4 = C / 4;
+        const int tcols = c4 < 256 ? c4 : 256, trows = 256 / tcols;
+        k_norm_act_v4<<<(unsigned)cdiv64(n, trows * NA_UNROLL), 256, 0, st>>>(x, (int)n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd,
+                                                                           slope, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo,
+                                                                           split_ld, tcols, trows);
+        PCRCG_CUDA(cudaGetLastError());
+        return PCRCG_OK;
+    }
     long long tot = (long long)n * ((C + 3) / 4);
     k_norm_act<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, mean, rstd, sc, C, sc_mean, sc_rstd, slope,
                                                           out, C, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, split_ld);

@@ -321,7 +321,7 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
 
 static bool g_pool_ready = false;
 
-static int pool_setup()
+int pool_setup()
 {
     if (g_pool_ready) return PCRCG_OK;
     int dev = 0;
