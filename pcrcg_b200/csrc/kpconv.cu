@@ -463,6 +463,55 @@ __global__ void __launch_bounds__(A64_WARPS * 32) k_kpconv_aggregate_mma64(
     if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few input channels (cin <= 4: the first layer has cin = 1): one THREAD per (query point, kernel point),
+// 16 threads per point.  Each thread walks the neighbour list once and keeps its kernel point's cin
+// accumulators; neighbour index / coordinates / features are broadcast loads inside the 16-thread group.
+template <typename IdxT, int CIN, bool SPLIT>
+__global__ void __launch_bounds__(256) k_kpconv_aggregate_small(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const float* __restrict__ x, int ldx, const uint8_t* __restrict__ rowflag, const float* __restrict__ kpts, int K,
+    float inv_extent, float* __restrict__ wf, __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo, int ldk,
+    float* __restrict__ inv_cnt)
+{
+    const int k = threadIdx.x & 15;
+    const int n = blockIdx.x * 16 + (threadIdx.x >> 4);
+    if (n >= nq) return;
+    const bool kok = k < K;
+    const int kk = kok ? k : 0;
+    const float kx = kpts[3 * kk] + q_pts[3 * (size_t)n], ky = kpts[3 * kk + 1] + q_pts[3 * (size_t)n + 1],
+                kz = kpts[3 * kk + 2] + q_pts[3 * (size_t)n + 2];
+    float acc[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; c++) acc[c] = 0.f;
+    int cnt = 0;
+    const IdxT* row = idx + (size_t)n * idx_stride;
+#pragma unroll 4
+    for (int h = 0; h < H; h++) {
+        const long long j = (long long)row[h];
+        if (j < 0 || j >= ns) continue;                      // uniform inside the 16-thread group
+        const float w = influence(s_pts + 3 * (size_t)j, kx, ky, kz, inv_extent);
+        const float* xr = x + (size_t)j * ldx;
+#pragma unroll
+        for (int c = 0; c < CIN; c++) acc[c] = fmaf(w, __ldg(xr + c), acc[c]);
+        cnt += rowflag[j];
+    }
+    if (kok) {
+#pragma unroll
+        for (int c = 0; c < CIN; c++) {
+            const size_t e = (size_t)n * ldk + (size_t)k * CIN + c;
+            if (SPLIT) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(acc[c]);
+                wf_hi[e] = h;
+                wf_lo[e] = __float2bfloat16_rn(acc[c] - __bfloat162float(h));
+            } else {
+                wf[e] = acc[c];
+            }
+        }
+    }
+    if (k == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
+}
+
 static int g_agg_simt = 0;
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
 
@@ -473,6 +522,17 @@ static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, co
 {
     dim3 block(AGG_WARPS * 32);
     unsigned gx = (unsigned)cdiv64(nq, AGG_WARPS);
+    if (cin <= 4 && !g_agg_simt) {
+#define PCRCG_AGG_SMALL(C_) k_kpconv_aggregate_small<IdxT, C_, SPLIT><<<(unsigned)cdiv64(nq, 16), 256, 0, st>>>( \
+        q_pts, nq, s_pts, ns, idx, H, idx_stride, x, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt)
+        if (cin == 1) PCRCG_AGG_SMALL(1);
+        else if (cin == 2) PCRCG_AGG_SMALL(2);
+        else if (cin == 3) PCRCG_AGG_SMALL(3);
+        else PCRCG_AGG_SMALL(4);
+#undef PCRCG_AGG_SMALL
+        PCRCG_CUDA(cudaGetLastError());
+        return PCRCG_OK;
+    }
     if (cin % 8 == 0 && ns > 0 && !g_agg_simt) {
 #define PCRCG_AGG_MMA(NT_) k_kpconv_aggregate_mma<IdxT, NT_, SPLIT><<<dim3(gx, (unsigned)(cin / (8 * NT_))), block, 0, st>>>( \
         q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt)
