@@ -8,7 +8,8 @@
 // feature tolerance with margin where a single bf16 (2e-3) or tf32 (3e-4 per op, 11 stacked blocks)
 // pass is not.
 //
-// Kernel (one 128 x BN output tile per CTA, 192 threads, 1 CTA/SM):
+// Kernel (PERSISTENT: one CTA per SM loops over 128 x BN output tiles, 192 threads; the accumulator is
+// double buffered in TMEM so the epilogue of tile i overlaps the TMA loads and MMAs of tile i+1):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor 2D loads of the four operand tiles of a
 //              64-wide K block (A_hi, A_lo [128 x 64], B_hi, B_lo [BN x 64], 128B swizzle) into a
 //              STAGES-deep shared-memory ring, mbarrier expect_tx / complete_tx
@@ -101,15 +102,21 @@ template <int BN> struct TcCfg {
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // 32, 64, 128 or 256
+    static constexpr int ACC_COLS = 2 * BN;                          // D1 | D2 of one accumulator set
+    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two sets: 64, 128, 256 or 512 columns
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                                              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                                                              float* __restrict__ C, int ldc, int M, int N, int K,
-                                                             const float* __restrict__ row_scale)
+                                                             const float* __restrict__ row_scale, int n_tiles_n, int total_tiles)
 {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -117,12 +124,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
     const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int num_kb = (K + TC_BK - 1) / TC_BK;
 
     if (warp == 0 && lane == 0) {
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -143,82 +150,103 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot_ptr;
+    const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
+        // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t st = base + s * Cfg::STAGE_BYTES;
-                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-                tma_load_2d(st, &map_a_hi, full_bar(s), kb * TC_BK, m0);
-                tma_load_2d(st + Cfg::A_BYTES, &map_a_lo, full_bar(s), kb * TC_BK, m0);
-                tma_load_2d(st + 2 * Cfg::A_BYTES, &map_b_hi, full_bar(s), kb * TC_BK, n0);
-                tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_b_lo, full_bar(s), kb * TC_BK, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * TC_BK, m0);
+                    tma_load_2d(st + Cfg::A_BYTES, &map_a_lo, full_bar(s), kb * TC_BK, m0);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &map_b_hi, full_bar(s), kb * TC_BK, n0);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_b_lo, full_bar(s), kb * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
+        // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc_cat = make_idesc(2 * BN);
             constexpr uint32_t idesc_one = make_idesc(BN);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++) {
+                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(acc), aph ^ 1u);          // epilogue has drained this accumulator set
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = base + s * Cfg::STAGE_BYTES;
-                const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + Cfg::A_BYTES), db = make_desc(st + 2 * Cfg::A_BYTES);
+                const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                    const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + Cfg::A_BYTES), db = make_desc(st + 2 * Cfg::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; k++) {
-                    const uint64_t adv = (uint64_t)((k * 32) >> 4);          // 16 bf16 = 32 bytes inside the swizzle atom
-                    umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_cat, (uint32_t)((kb | k) != 0));
-                    umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1u);
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 bf16 = 32 bytes inside the swizzle atom
+                        umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_cat, (uint32_t)((kb | k) != 0));
+                        umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1u);
+                    }
+                    umma_commit(empty_bar(s));
                 }
-                umma_commit(empty_bar(s));
+                umma_commit(tmem_full_bar(acc));
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(tmem_full_bar, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float sc = (row_scale != nullptr && row < M) ? row_scale[row] : 1.0f;
-        const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++) {
+            const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
+            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            const int row = m0 + q * 32 + lane;
+            mbar_wait(tmem_full_bar(acc), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float sc = (row_scale != nullptr && row < M) ? row_scale[row] : 1.0f;
+            const uint32_t trow = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            if (n0 + c >= N) break;                      // warp-uniform
-            uint32_t d1[16], d2[16];
-            tmem_ld16(trow + (uint32_t)c, d1);
-            tmem_ld16(trow + (uint32_t)(BN + c), d2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float* o = C + (size_t)row * ldc + n0 + c;
-                if (n0 + c + 16 <= N && (ldc & 3) == 0) {
+            for (int c = 0; c < BN; c += 16) {
+                if (n0 + c >= N) break;                      // warp-uniform
+                uint32_t d1[16], d2[16];
+                tmem_ld16(trow + (uint32_t)c, d1);
+                tmem_ld16(trow + (uint32_t)(BN + c), d2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+                    float* o = C + (size_t)row * ldc + n0 + c;
+                    if (n0 + c + 16 <= N && (ldc & 3) == 0) {
 #pragma unroll
-                    for (int u = 0; u < 16; u += 4) {
-                        float4 v;
-                        v.x = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
-                        v.y = (__uint_as_float(d1[u + 1]) + __uint_as_float(d2[u + 1])) * sc;
-                        v.z = (__uint_as_float(d1[u + 2]) + __uint_as_float(d2[u + 2])) * sc;
-                        v.w = (__uint_as_float(d1[u + 3]) + __uint_as_float(d2[u + 3])) * sc;
-                        *reinterpret_cast<float4*>(o + u) = v;
+                        for (int u = 0; u < 16; u += 4) {
+                            float4 v;
+                            v.x = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
+                            v.y = (__uint_as_float(d1[u + 1]) + __uint_as_float(d2[u + 1])) * sc;
+                            v.z = (__uint_as_float(d1[u + 2]) + __uint_as_float(d2[u + 2])) * sc;
+                            v.w = (__uint_as_float(d1[u + 3]) + __uint_as_float(d2[u + 3])) * sc;
+                            *reinterpret_cast<float4*>(o + u) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 16; u++)
+                            if (n0 + c + u < N) o[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
                     }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 16; u++)
-                        if (n0 + c + u < N) o[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -313,8 +341,11 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
         PCRCG_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid((unsigned)cdiv64(M, TC_BM), (unsigned)cdiv64(N, BN));
-    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale);
+    const int n_tiles_n = (int)cdiv64(N, BN);
+    const long long total = cdiv64(M, TC_BM) * n_tiles_n;
+    PCRCG_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
+    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);      // persistent: one CTA per SM
+    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale, n_tiles_n, (int)total);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }
