@@ -8,8 +8,9 @@
 //
 // Grid: per cloud, cell edge cs = radius*(1+1e-3) + 8*ulp(max|coord|) so that any pair accepted by
 // the fp32 distance test lies in adjacent cells despite rounding in the cell computation.  Occupied
-// cells live in an open-addressing table (2*Ns+1 slots per cloud); supports are radix-sorted by
-// table slot so each cell is one contiguous run of (x,y,z,index) float4 records.
+// cells live in an open-addressing table (2*Ns+1 slots per cloud); supports are bucketed by
+// table slot (counting sort: per-slot count, exclusive scan, atomic cursor) so each cell is one
+// contiguous run of (x,y,z,index) float4 records.
 //
 // Search kernel: one warp per query.  Lanes 0..26 resolve the 27 adjacent cells, the warp then
 // walks the concatenated candidate runs 32 at a time, tests d2 and compacts hits with
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float* __restrict__ s, 
 
 __global__ void __launch_bounds__(256) k_cell_insert(const uint64_t* __restrict__ keys, int ns, const int32_t* __restrict__ sstarts,
                                                      int nb, uint32_t* __restrict__ rep, uint32_t* __restrict__ slot,
-                                                     uint32_t* __restrict__ iota)
+                                                     uint32_t* __restrict__ cell_count)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
@@ -120,20 +121,23 @@ __global__ void __launch_bounds__(256) k_cell_insert(const uint64_t* __restrict_
         h = h + 1u == cap ? 0u : h + 1u;
     }
     slot[i] = toff + h;
-    iota[i] = (uint32_t)i;
+    atomicAdd(&cell_count[toff + h], 1u);
 }
 
-// sorted records + per-slot [start,end)
-__global__ void __launch_bounds__(256) k_cell_runs(const float* __restrict__ s, const uint32_t* __restrict__ sslot,
-                                                   const uint32_t* __restrict__ sidx, int ns, float4* __restrict__ rec,
-                                                   uint2* __restrict__ range)
+// Counting sort by cell slot: cell_start = exclusive scan of cell_count; every point takes the next free
+// position of its cell.  The order INSIDE a cell is arbitrary (atomic cursor) -- harmless: rows are sorted by
+// (d2, index) afterwards, so results do not depend on it.
+__global__ void __launch_bounds__(256) k_cell_scatter(const float* __restrict__ s, const uint32_t* __restrict__ slot, int ns,
+                                                      const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor,
+                                                      float4* __restrict__ rec, uint2* __restrict__ range)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ns) return;
-    uint32_t sl = sslot[j], p = sidx[j];
-    rec[j] = make_float4(s[3 * (size_t)p], s[3 * (size_t)p + 1], s[3 * (size_t)p + 2], __uint_as_float(p));
-    if (j == 0 || sslot[j - 1] != sl) range[sl].x = (uint32_t)j;
-    if (j == ns - 1 || sslot[j + 1] != sl) range[sl].y = (uint32_t)(j + 1);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const uint32_t sl = slot[i];
+    const uint32_t st = cell_start[sl];
+    const uint32_t k = atomicAdd(&cursor[sl], 1u);
+    rec[st + k] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
+    if (k == 0) range[sl] = make_uint2(st, cell_start[sl + 1]);
 }
 
 __device__ __forceinline__ float d2_ref(float qx, float qy, float qz, float4 p)
@@ -365,11 +369,11 @@ static size_t rad_layout(Workspace& W, int64_t ns, int32_t nb, RadWS* o)
     r.rep = W.take<uint32_t>(2 * n1 + nb);
     r.range = W.take<uint2>(2 * n1 + nb);
     r.slot = W.take<uint32_t>(n1);
-    r.iota = W.take<uint32_t>(n1);
-    r.sslot = W.take<uint32_t>(n1);
-    r.sidx = W.take<uint32_t>(n1);
+    r.iota = W.take<uint32_t>(2 * n1 + nb + 1);        // per-slot cursor
+    r.sslot = W.take<uint32_t>(2 * n1 + nb + 2);       // per-slot count -> start (exclusive scan, +1 total)
+    r.sidx = W.take<uint32_t>(1);
     r.rec = W.take<float4>(n1);
-    r.prim_bytes = sort_ws_bytes(ns);
+    r.prim_bytes = scan_ws_bytes(2 * (int64_t)n1 + nb + 1);
     r.prim = W.take<char>(r.prim_bytes);
     if (o) *o = r;
     return W.off;
@@ -396,19 +400,20 @@ int radius_build_dev(const float* s, int64_t ns, const int32_t* s_lens, int32_t 
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "radius search: workspace too small (%zu < %zu)", ws_bytes, W.off);
     const int NS = (int)ns;
     const unsigned gs = (unsigned)cdiv64(NS > 0 ? NS : 1, 256);
-    int nbits = 1;
-    while ((1ull << nbits) < 2ull * (uint64_t)NS + (uint64_t)nb + 1ull) nbits++;
-    ProfScope prof(PC_RADIUS_BUILD, st, 8 + 5 * ((nbits + 7) / 8));
+    ProfScope prof(PC_RADIUS_BUILD, st, 11);
+    const size_t nslots = 2 * (size_t)NS + nb;
     PCRCG_TRY(cloud_starts(s_lens, nb, r.sstarts, st));
     k_rbbox_init<<<(nb * 6 + 255) / 256, 256, 0, st>>>(r.bbox, nb);
     k_rbbox<<<gs, 256, 0, st>>>(s, NS, r.sstarts, nb, r.bbox);
     k_grid_meta<<<(nb + 127) / 128, 128, 0, st>>>(r.bbox, nb, radius, r.meta);
     k_cell_keys<<<gs, 256, 0, st>>>(s, NS, r.sstarts, nb, r.meta, r.keys);
-    PCRCG_CUDA(cudaMemsetAsync(r.rep, 0xff, sizeof(uint32_t) * (2 * (size_t)NS + nb), st));
-    k_cell_insert<<<gs, 256, 0, st>>>(r.keys, NS, r.sstarts, nb, r.rep, r.slot, r.iota);
+    PCRCG_CUDA(cudaMemsetAsync(r.rep, 0xff, sizeof(uint32_t) * nslots, st));
+    PCRCG_CUDA(cudaMemsetAsync(r.iota, 0, sizeof(uint32_t) * (nslots + 1), st));
+    PCRCG_CUDA(cudaMemsetAsync(r.sslot, 0, sizeof(uint32_t) * (nslots + 2), st));
+    k_cell_insert<<<gs, 256, 0, st>>>(r.keys, NS, r.sstarts, nb, r.rep, r.slot, r.sslot);
     PCRCG_CUDA(cudaGetLastError());
-    PCRCG_TRY(radix_sort_pairs(r.slot, r.iota, r.sslot, r.sidx, NS, nbits, r.prim, r.prim_bytes, st));
-    k_cell_runs<<<gs, 256, 0, st>>>(s, r.sslot, r.sidx, NS, r.rec, r.range);
+    PCRCG_TRY(exclusive_scan_u32(r.sslot, r.sslot, (int64_t)nslots, r.prim, r.prim_bytes, st));
+    k_cell_scatter<<<gs, 256, 0, st>>>(s, r.slot, NS, r.sslot, r.iota, r.rec, r.range);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

@@ -60,6 +60,7 @@ def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pai
     out = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[])
     pending, counts_out = [], []            # (list name, layer, rows, limit, max_count tensor)
     layer, layer_blocks = 0, []
+    next_grid = None          # the upsample grid of level l (coarse points, radius 2r) is the conv/pool grid of level l+1
     for block_i, block in enumerate(arch):
         if "global" in block or "upsample" in block:
             break
@@ -68,9 +69,11 @@ def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pai
             if block_i < len(arch) - 1 and "upsample" not in arch[block_i + 1]:
                 continue
         limit = int(neighborhood_limits[layer])
-        grid_fine = None
+        grid_fine = next_grid
+        next_grid = None
         if layer_blocks:
-            grid_fine = ops.RadiusGrid(pts, lens, r_normal)
+            if grid_fine is None:
+                grid_fine = ops.RadiusGrid(pts, lens, r_normal)
             conv_i, cnt, mx = grid_fine.query(pts, lens, limit, want_counts=return_counts)
             pending.append(("neighbors", layer, conv_i, limit, mx))
             counts_out.append(cnt)
@@ -83,7 +86,8 @@ def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pai
                 grid_fine = ops.RadiusGrid(pts, lens, r_normal)
             pool_i, _, mxp = grid_fine.query(pool_p, pool_b, limit, want_counts=False)
             pending.append(("pools", layer, pool_i, limit, mxp))
-            up_i, _, mxu = ops.RadiusGrid(pool_p, pool_b, 2 * r_normal).query(pts, lens, limit, want_counts=False)
+            next_grid = ops.RadiusGrid(pool_p, pool_b, 2 * r_normal)
+            up_i, _, mxu = next_grid.query(pts, lens, limit, want_counts=False)
             pending.append(("upsamples", layer, up_i, limit, mxu))
         else:
             pool_i = torch.zeros((0, 1), dtype=torch.int32, device=device)
