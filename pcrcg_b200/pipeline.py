@@ -62,17 +62,55 @@ class FeaturePath:
     def run_host(self, points_host, lengths_host, out_host=None):
         """HOST buffers in and out.  points_host [N,3] f32 (pinned for async copies), lengths_host [2P] i32.
         Returns (features_host [N3,C], lengths of the coarsest level [2P] on the host)."""
+        h = self.submit_host(points_host, lengths_host, out_host)
+        return h.result()
+
+    @torch.no_grad()
+    def submit_host(self, points_host, lengths_host, out_host=None):
+        """Pipelined form of :meth:`run_host`: the device->host copy of the result runs on a separate copy
+        stream, so it overlaps the next submission's compute.  Returns a handle; ``handle.result()`` waits for
+        this submission only.  ``out_host`` (pinned, reused by the caller once result() returned) avoids a
+        pageable copy."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pinned_small, self._slot = {}, 0
         pts = points_host.to(self.device, non_blocking=True)
         lens = lengths_host.to(self.device, non_blocking=True)
         y, batch = self.run_device(pts, lens)
-        if out_host is not None and out_host.shape[0] >= y.shape[0]:
-            out = out_host[:y.shape[0]]
-            out.copy_(y, non_blocking=True)
-        else:
-            out = y.cpu()
-        coarse = batch["stack_lengths"][-1].cpu()
-        torch.cuda.current_stream().synchronize()
-        return out, coarse
+        coarse_dev = batch["stack_lengths"][-1]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            if out_host is not None and out_host.shape[0] >= y.shape[0]:
+                out = out_host[:y.shape[0]]
+            else:
+                out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+            # in 4 MB pieces: the pyramid's small size read-backs of the NEXT submission share the D2H copy
+            # engine and would otherwise queue behind one monolithic transfer
+            step = max(1, (4 << 20) // max(1, y.shape[1] * 4))
+            for r in range(0, y.shape[0], step):
+                out[r:r + step].copy_(y[r:r + step], non_blocking=True)
+            self._slot ^= 1                      # small pinned staging buffers are cached (pinned allocation is slow)
+            key = (self._slot, tuple(coarse_dev.shape))
+            if key not in self._pinned_small:
+                self._pinned_small[key] = torch.empty(coarse_dev.shape, dtype=coarse_dev.dtype, pin_memory=True)
+            coarse = self._pinned_small[key]
+            coarse.copy_(coarse_dev, non_blocking=True)
+            y.record_stream(self._copy_stream)
+            coarse_dev.record_stream(self._copy_stream)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        return _HostResult(out, coarse, done)
+
+
+class _HostResult:
+    def __init__(self, out, coarse, done):
+        self._out, self._coarse, self._done = out, coarse, done
+
+    def result(self):
+        self._done.synchronize()
+        return self._out, self._coarse
 
 
 def stack_pairs(pairs):
