@@ -86,6 +86,14 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
                              const float* kernel_points, int32_t K, float KP_extent, const float* weights, int32_t cout,
                              float* out, void* ws, size_t ws_bytes, pcrcg_stream_t stream);
 
+/* Same, with the features ALSO available as bf16 (hi, lo) planes [ns, ldxs] (x = hi + lo; emitted by
+ * pcrcg_norm_act_dev): the aggregation then runs its bf16x3 ldmatrix / mma.m16n8k16 kernel. */
+int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
+                                   int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi,
+                                   const void* x_lo, int32_t ldxs, int32_t cin, const float* kernel_points, int32_t K,
+                                   float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
+                                   pcrcg_stream_t stream);
+
 /* Dense contraction C[M,N] = A[M,K] * B (* row_scale[m] if not NULL).  B is [K,N] (b_is_nk = 0) or
  * [N,K] (b_is_nk = 1, nn.Linear.weight of models/blocks.py:490).  Row-major, leading dims in elements. */
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc,

@@ -110,8 +110,8 @@ class UnaryBlock(nn.Module):
         self.mlp = _Linear(in_dim, out_dim)
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
-    def forward(self, x, batch=None, segments=None):
-        return self.batch_norm(self.mlp(x), segments, None if self.no_relu else 0.1)
+    def forward(self, x, batch=None, segments=None, emit_split=False):
+        return self.batch_norm(self.mlp(x), segments, None if self.no_relu else 0.1, emit_split=emit_split)
 
 
 class LastUnaryBlock(nn.Module):
@@ -168,7 +168,8 @@ class ResnetBottleneckBlock(nn.Module):
     def forward(self, features, batch):
         q_pts, s_pts, inds, out_layer = _block_geometry(self.block_name, self.layer_ind, batch)
         seg_in, seg_out = _segments(batch, self.layer_ind), _segments(batch, out_layer)
-        x = self.unary1(features, segments=seg_in) if isinstance(self.unary1, UnaryBlock) else features
+        # unary1's output is gathered by the KPConv aggregation: emit its bf16 planes for the bf16x3 kernel
+        x = self.unary1(features, segments=seg_in, emit_split=True) if isinstance(self.unary1, UnaryBlock) else features
         x = self.KPConv(q_pts, s_pts, inds, x)
         x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True)                  # feeds unary2
         y = self.unary2.mlp(x)                                       # raw Linear; its norm is fused below

@@ -512,6 +512,166 @@ __global__ void __launch_bounds__(256) k_kpconv_aggregate_small(
     if (k == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// bf16x3 variant of the 64-channel-slab tensor-core aggregation, used when the producer of the features
+// already emitted them as bf16 (hi, lo) planes (instance norm epilogue, dense.cu).  Compared with the
+// 3xTF32 kernel above: mma.sync m16n8k16 (16 neighbours per step: half the MMAs), B fragments come
+// straight out of shared memory with ldmatrix.trans (no per-use hi/lo splitting), and the result tile is
+// transposed through shared memory with stmatrix so the bf16 planes are written in whole 128-byte rows.
+//   A (influence weights, split hi/lo in registers) x B (feature planes hi / lo):  hi*hi + hi*lo + lo*hi
+constexpr int AB_WARPS = 4;
+constexpr int AB_ROWS = 32;                    // neighbours staged per chunk = 2 k-steps of 16
+constexpr int AB_PITCH = 144;                  // bytes per staged plane row (128 + 16: conflict-free ldmatrix)
+constexpr int AB_WARP_BYTES = 2 * AB_ROWS * AB_PITCH + AB_ROWS * 16;    // hi plane, lo plane, coordinates
+constexpr int AB_SMEM = AB_WARPS * AB_WARP_BYTES;
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// packs (lo half = a, hi half = b) as bf16x2 and returns the residuals
+__device__ __forceinline__ uint32_t pack_split(float a, float b, uint32_t& lo_packed)
+{
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    lo_packed = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo, int cin, int ldxs,
+    const uint8_t* __restrict__ rowflag, const float* __restrict__ kpts, int K, float inv_extent,
+    __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo, int ldk, float* __restrict__ inv_cnt)
+{
+    extern __shared__ __align__(16) uint8_t smem_b[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * AB_WARPS + w;
+    if (n >= nq) return;
+    uint8_t* s_hi = smem_b + (size_t)w * AB_WARP_BYTES;
+    uint8_t* s_lo = s_hi + AB_ROWS * AB_PITCH;
+    float* s_xyz = reinterpret_cast<float*>(s_lo + AB_ROWS * AB_PITCH);      // [row][x,y,z,valid]
+    const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(s_hi), a_lo = (uint32_t)__cvta_generic_to_shared(s_lo);
+    const int g = lane >> 2, t = lane & 3;
+    const int c0 = blockIdx.y * 64;
+
+    const float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
+    const bool k1ok = g + 8 < K, k0ok = g < K;
+    const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
+    const float k0x = kpts[3 * ka] + qx, k0y = kpts[3 * ka + 1] + qy, k0z = kpts[3 * ka + 2] + qz;
+    const float k1x = kpts[3 * kb] + qx, k1y = kpts[3 * kb + 1] + qy, k1z = kpts[3 * kb + 2] + qz;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    int cnt = 0;
+    const IdxT* row = idx + (size_t)n * idx_stride;
+    // staging: lanes 0..7 copy the 8 x 16-byte chunks of a hi row, 8..15 of the lo row; lanes 16..31 the next neighbour
+    const int chunk = lane & 7, plane = (lane >> 3) & 1, rsel = lane >> 4;
+    const __nv_bfloat16* xp = (plane ? x_lo : x_hi) + c0 + chunk * 8;
+    uint8_t* sp_dst = (plane ? s_lo : s_hi) + chunk * 16;
+    // ldmatrix lane addressing: matrix m = lane>>3 -> (k half = m&1, n-tile offset = m>>1), row = lane&7
+    const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
+
+    for (int h0 = 0; h0 < H; h0 += AB_ROWS) {
+        int ja = ns;
+        if (h0 + lane < H) { long long v = (long long)row[h0 + lane]; ja = (v >= 0 && v < ns) ? (int)v : ns; }
+        const bool va = ja < ns;
+        {
+            float* d = s_xyz + lane * 4;
+            const float* sp = s_pts + 3 * (size_t)(va ? ja : 0);
+            cp_async4(d, sp, va); cp_async4(d + 1, sp + 1, va); cp_async4(d + 2, sp + 2, va);
+            d[3] = va ? 1.f : 0.f;
+        }
+#pragma unroll 4
+        for (int r = 0; r < AB_ROWS; r += 2) {
+            const int rr = r + rsel;
+            const int j = __shfl_sync(0xffffffffu, ja, rr);
+            const bool v = j < ns;
+            cp_async16(sp_dst + rr * AB_PITCH, xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs), v);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (blockIdx.y == 0) cnt += __popc(__ballot_sync(0xffffffffu, va && rowflag[ja] != 0));
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+
+#pragma unroll
+        for (int s = 0; s < AB_ROWS / 16; s++) {
+            if (h0 + 16 * s >= H) break;                    // warp-uniform
+            // A fragment: kernel points (g, g+8) x neighbours (2t, 2t+1 | 2t+8, 2t+9) of this 16-neighbour step
+            float wv[2][4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int rn = 16 * s + 2 * t + (e & 1) + (e >> 1) * 8;
+                const float4 p = *reinterpret_cast<const float4*>(s_xyz + rn * 4);
+                const float sa[3] = { p.x, p.y, p.z };
+                wv[0][e] = (p.w != 0.f && k0ok) ? influence(sa, k0x, k0y, k0z, inv_extent) : 0.f;
+                wv[1][e] = (p.w != 0.f && k1ok) ? influence(sa, k1x, k1y, k1z, inv_extent) : 0.f;
+            }
+            uint32_t ahi[4], alo[4];
+            ahi[0] = pack_split(wv[0][0], wv[0][1], alo[0]);     // row g   , k 2t..2t+1
+            ahi[1] = pack_split(wv[1][0], wv[1][1], alo[1]);     // row g+8 , k 2t..2t+1
+            ahi[2] = pack_split(wv[0][2], wv[0][3], alo[2]);     // row g   , k 2t+8..2t+9
+            ahi[3] = pack_split(wv[1][2], wv[1][3], alo[3]);     // row g+8 , k 2t+8..2t+9
+            const uint32_t sbase = (uint32_t)(16 * s) * AB_PITCH + lm_off;
+#pragma unroll
+            for (int np = 0; np < 4; np++) {                      // pairs of n-tiles (2 x 8 channels = 32 bytes)
+                uint32_t bh[4], bl[4];
+                ldmatrix_x4_trans(bh, a_hi + sbase + np * 32);
+                ldmatrix_x4_trans(bl, a_lo + sbase + np * 32);
+                mma_bf16(acc[2 * np], alo, bh[0], bh[1]);
+                mma_bf16(acc[2 * np], ahi, bl[0], bl[1]);
+                mma_bf16(acc[2 * np], ahi, bh[0], bh[1]);
+                mma_bf16(acc[2 * np + 1], alo, bh[2], bh[3]);
+                mma_bf16(acc[2 * np + 1], ahi, bl[2], bl[3]);
+                mma_bf16(acc[2 * np + 1], ahi, bh[2], bh[3]);
+            }
+        }
+        __syncwarp();
+    }
+    // D tile [16 kp x 64 ch] -> bf16 hi / lo -> shared (stmatrix, row pitch AB_PITCH) -> global rows of 128 bytes.
+    // stmatrix.x4: matrix m = lane>>3 supplies row addresses; we store (kp 0-7 | 8-15) x (n-tile 2np, 2np+1).
+    {
+        const uint32_t st_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
+#pragma unroll
+        for (int np = 0; np < 4; np++) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {        // q: 0 = (rows 0-7, tile 2np), 1 = (rows 8-15, tile 2np), 2 = (rows 0-7, tile 2np+1), 3 = (rows 8-15, 2np+1)
+                const int tile = 2 * np + (q >> 1), rh = q & 1;
+                h[q] = pack_split(acc[tile][2 * rh], acc[tile][2 * rh + 1], l[q]);
+            }
+            stmatrix_x4(a_hi + st_off + np * 32, h[0], h[1], h[2], h[3]);
+            stmatrix_x4(a_lo + st_off + np * 32, l[0], l[1], l[2], l[3]);
+        }
+        __syncwarp();
+        // 16 rows x 128 bytes per plane: 8 lanes per row, 4 rows per instruction
+        const int rl = lane >> 3, cl = lane & 7;
+#pragma unroll
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+            const int kp = r0 + rl;
+            if (kp < K) {
+                const size_t e = (size_t)n * ldk + (size_t)kp * cin + c0 + cl * 8;
+                *reinterpret_cast<uint4*>(wf_hi + e) = *reinterpret_cast<const uint4*>(s_hi + kp * AB_PITCH + cl * 16);
+                *reinterpret_cast<uint4*>(wf_lo + e) = *reinterpret_cast<const uint4*>(s_lo + kp * AB_PITCH + cl * 16);
+            }
+        }
+    }
+    if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
+}
+
 static int g_agg_simt = 0;
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
 
@@ -600,7 +760,8 @@ size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 // weights: [K, cin, cout] row-major (the reference's Parameter layout)
 int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* idx, int idx_is_i64, int32_t H,
                        int32_t idx_stride, const float* x, int32_t cin, const float* kpts, int32_t K, float kp_extent,
-                       const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes, cudaStream_t st)
+                       const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                       const void* x_hi, const void* x_lo, int32_t ldxs)
 {
     PCRCG_REQUIRE(K >= 1 && K <= KP_MAX - 1, "kpconv: kernel_size must be in [1,15]");
     PCRCG_REQUIRE(cin >= 1 && cout >= 1 && cout <= 2048 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
@@ -643,7 +804,18 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
         {
             ProfScope prof(PC_KPCONV_AGG, st, 1);
             int rc;
-            if (idx_is_i64) {
+            const bool planes = tc && x_hi != nullptr && x_lo != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 && !g_agg_simt && ns > 0;
+            if (planes) {
+                dim3 grid((unsigned)cdiv64(rows, AB_WARPS), (unsigned)(cin / 64));
+                if (idx_is_i64)
+                    k_kpconv_aggregate_bf16<long long><<<grid, AB_WARPS * 32, AB_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                else
+                    k_kpconv_aggregate_bf16<int><<<grid, AB_WARPS * 32, AB_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                rc = cudaGetLastError() == cudaSuccess ? PCRCG_OK : PCRCG_ERR;
+                if (rc) set_error("kpconv: bf16 aggregate launch failed");
+            } else if (idx_is_i64) {
                 rc = tc ? launch_agg<long long, true>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, nullptr, wf_hi, wf_lo, ldk, inv_cnt + r0, st)
                         : launch_agg<long long, false>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride, x, cin, cin, rowflag, kpts, K, inv_extent, wf, nullptr, nullptr, ldk, inv_cnt + r0, st);
             } else {

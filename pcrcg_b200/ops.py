@@ -118,9 +118,17 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
     with torch.cuda.device(dev):
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         ws = _ws(L.pcrcg_kpconv_ws_bytes(nq, ns, cin, K), dev)
-        check(L.pcrcg_kpconv_forward_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
-                                         x.data_ptr(), cin, kernel_points.data_ptr(), K, float(KP_extent), weights.data_ptr(),
-                                         cout, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        sp = getattr(x, "_pcrcg_split", None)
+        if sp is not None and not _force_simt:
+            hi, lo, ld = sp
+            check(L.pcrcg_kpconv_forward_split_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
+                                                   x.data_ptr(), hi.data_ptr(), lo.data_ptr(), ld, cin, kernel_points.data_ptr(), K,
+                                                   float(KP_extent), weights.data_ptr(), cout, out.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), _stream()))
+        else:
+            check(L.pcrcg_kpconv_forward_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
+                                             x.data_ptr(), cin, kernel_points.data_ptr(), K, float(KP_extent), weights.data_ptr(),
+                                             cout, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
     return out
 
 

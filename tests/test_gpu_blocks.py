@@ -138,3 +138,23 @@ def test_multi_pair_batch_equals_single_pairs(contraction_path):
         assert part.shape == s.shape
         # bf16x3 operand splitting is not smooth in its inputs: stacked vs single differ at its 1e-5 error level
         assert np.abs(part - s).max() <= (2e-5 if contraction_path == "simt" else 3e-4) * np.abs(s).max()
+
+
+@pytest.mark.parametrize("cin,cout,H", [(64, 64, 34), (128, 64, 39), (256, 128, 17), (64, 32, 70)])
+def test_kpconv_bf16_plane_path_vs_port(cin, cout, H, contraction_path):
+    """Features produced by the InstanceNorm epilogue carry bf16 (hi, lo) planes; the aggregation then takes its
+    ldmatrix / mma.m16n8k16 bf16x3 kernel.  Same tolerance as every other path."""
+    src, tgt, _ = synthetic.match3d_pair(7, n_target=1300)
+    pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+    radius = 0.0625 if H < 60 else 0.09
+    rows = ops.batch_query(_d(pts), _d(pts), _d(lens), _d(lens), radius, H)
+    g = torch.Generator().manual_seed(cin + H)
+    raw = torch.randn(len(pts), cin, generator=g).to(DEV)
+    x = ops.instance_norm_act(raw, None, 0.1, emit_split=True)
+    assert contraction_path == "simt" or hasattr(x, "_pcrcg_split")
+    w = torch.randn(15, cin, cout, generator=g) / np.sqrt(15 * cin)
+    kp = torch.randn(15, 3, generator=g) * 0.03
+    ref = bp.kpconv(torch.from_numpy(pts), torch.from_numpy(pts), rows.cpu(), x.cpu(), kp, w, 0.05)
+    out = ops.kpconv_forward(_d(pts), _d(pts), rows, x, kp.to(DEV), w.to(DEV), 0.05)
+    assert _err(out, ref) < TOL
+    assert _err(out, ref) < 1e-4      # the split schemes are fp32-class, far inside the tolerance
