@@ -90,7 +90,8 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
  * pcrcg_norm_act_dev): the aggregation then runs its bf16x3 ldmatrix / mma.m16n8k16 kernel. */
 int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
                                    int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi,
-                                   const void* x_lo, int32_t ldxs, int32_t cin, const float* kernel_points, int32_t K,
+                                   const void* x_lo, int32_t ldxs, const uint8_t* row_positive /* may be NULL */, int32_t cin,
+                                   const float* kernel_points, int32_t K,
                                    float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
                                    pcrcg_stream_t stream);
 
@@ -119,12 +120,15 @@ int pcrcg_set_option(const char* name, int32_t value);
  *   act = LeakyReLU(slope) when slope >= 0, identity when slope < 0;  mean == NULL skips the normalisation.
  * split_hi / split_lo (bf16 [n, split_ld], may be NULL): the result is ALSO emitted as the (hi, lo) planes the
  * next tensor-core contraction consumes, saving that contraction's own split pass.
+ * row_positive (uint8 [n], may be NULL; needs a power-of-two C): flag[r] = (sum_c out[r,c] > 0), the per-row
+ * predicate of the KPConv neighbour count (models/blocks.py:369-370), saving the consumer a pass over out.
  * ------------------------------------------------------------------------------------------- */
 int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps,
                        float* mean, float* rstd, pcrcg_stream_t stream);
 int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
                        const float* rstd, const float* sc, const float* sc_mean, const float* sc_rstd, float slope,
-                       float* out, void* split_hi, void* split_lo, int32_t split_ld, pcrcg_stream_t stream);
+                       float* out, void* split_hi, void* split_lo, int32_t split_ld, uint8_t* row_positive,
+                       pcrcg_stream_t stream);
 
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,

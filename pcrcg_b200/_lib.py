@@ -36,14 +36,14 @@ SIGNATURES = {
     "pcrcg_batch_query_host": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _F, _I32, C.POINTER(_P), C.POINTER(_I32)]),
     "pcrcg_kpconv_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "pcrcg_kpconv_forward_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),
-    "pcrcg_kpconv_forward_split_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),
+    "pcrcg_kpconv_forward_split_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),
     "pcrcg_gemm_dev": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "pcrcg_split_bf16_dev": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _I32, _P]),
     "pcrcg_gemm_bf16x3_dev": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "pcrcg_set_option": (C.c_int, [C.c_char_p, _I32]),
     "pcrcg_gemm_force_simt": (None, [_I32]),
     "pcrcg_colstats_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _F, _P, _P, _P]),
-    "pcrcg_norm_act_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I32, _P]),
+    "pcrcg_norm_act_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I32, _P, _P]),
     "pcrcg_max_pool_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _I64, _I32, _I32, _P, _P]),
     "pcrcg_projection_ws_bytes": (_SZ, [_I64]),
     "pcrcg_projection_dev": (C.c_int, [_P, _I64, _P, _I32, _I32, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),

@@ -83,9 +83,9 @@ class BatchNormBlock(nn.Module):
         if not use_bn:
             self.bias = Parameter(torch.zeros(in_dim, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, x, segments=None, slope=None, emit_split=False):
+    def forward(self, x, segments=None, slope=None, emit_split=False, emit_rowpos=False):
         if self.use_bn:
-            return ops.instance_norm_act(x, segments, slope, emit_split=emit_split)
+            return ops.instance_norm_act(x, segments, slope, emit_split=emit_split, emit_rowpos=emit_rowpos)
         x = x + self.bias
         return x if slope is None else torch.nn.functional.leaky_relu(x, slope)
 
@@ -110,8 +110,8 @@ class UnaryBlock(nn.Module):
         self.mlp = _Linear(in_dim, out_dim)
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
-    def forward(self, x, batch=None, segments=None, emit_split=False):
-        return self.batch_norm(self.mlp(x), segments, None if self.no_relu else 0.1, emit_split=emit_split)
+    def forward(self, x, batch=None, segments=None, emit_split=False, emit_rowpos=False):
+        return self.batch_norm(self.mlp(x), segments, None if self.no_relu else 0.1, emit_split=emit_split, emit_rowpos=emit_rowpos)
 
 
 class LastUnaryBlock(nn.Module):
@@ -169,7 +169,7 @@ class ResnetBottleneckBlock(nn.Module):
         q_pts, s_pts, inds, out_layer = _block_geometry(self.block_name, self.layer_ind, batch)
         seg_in, seg_out = _segments(batch, self.layer_ind), _segments(batch, out_layer)
         # unary1's output is gathered by the KPConv aggregation: emit its bf16 planes for the bf16x3 kernel
-        x = self.unary1(features, segments=seg_in, emit_split=True) if isinstance(self.unary1, UnaryBlock) else features
+        x = self.unary1(features, segments=seg_in, emit_split=True, emit_rowpos=True) if isinstance(self.unary1, UnaryBlock) else features
         x = self.KPConv(q_pts, s_pts, inds, x)
         x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True)                  # feeds unary2
         y = self.unary2.mlp(x)                                       # raw Linear; its norm is fused below

@@ -55,7 +55,7 @@ int radius_query_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, fl
 
 size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K);
 int kpconv_forward_dev(const float*, int64_t, const float*, int64_t, const void*, int, int32_t, int32_t, const float*, int32_t, const float*,
-                       int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t, const void*, const void*, int32_t);
+                       int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t, const void*, const void*, int32_t, const uint8_t*);
 int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
 void gemm_set_force_simt(int);
 void dense_set_norm_v4(int);
@@ -64,7 +64,7 @@ int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, fl
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
 int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
-                 const float*, float, float*, void*, void*, int32_t, cudaStream_t);
+                 const float*, float, float*, void*, void*, int32_t, uint8_t*, cudaStream_t);
 int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
@@ -213,16 +213,17 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
                              pcrcg_stream_t stream)
 {
     return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
-                              cout, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr);
 }
 
 int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
                                    int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi, const void* x_lo,
-                                   int32_t ldxs, int32_t cin, const float* kernel_points, int32_t K, float KP_extent, const float* weights,
-                                   int32_t cout, float* out, void* ws, size_t ws_bytes, pcrcg_stream_t stream)
+                                   int32_t ldxs, const uint8_t* row_positive, int32_t cin, const float* kernel_points, int32_t K,
+                                   float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
+                                   pcrcg_stream_t stream)
 {
     return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
-                              cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs);
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs, row_positive);
 }
 
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc, int32_t M, int32_t N,
@@ -262,9 +263,9 @@ int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
 
 int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
                        const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
-                       int32_t split_ld, pcrcg_stream_t stream)
+                       int32_t split_ld, uint8_t* row_positive, pcrcg_stream_t stream)
 {
-    return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld,
+    return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld, row_positive,
                         (cudaStream_t)stream);
 }
 

@@ -125,9 +125,12 @@ __global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x
                                                      const float* __restrict__ sc, const float* __restrict__ sc_mean,
                                                      const float* __restrict__ sc_rstd, float slope, float* __restrict__ out,
                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int lds,
-                                                     int tcols, int trows)
+                                                     int tcols, int trows, uint8_t* __restrict__ rowflag)
 {
     const int c4 = C >> 2;
+    float rsum[NA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NA_UNROLL; u++) rsum[u] = 0.f;
     const int tx = threadIdx.x % tcols, ty = threadIdx.x / tcols;
     if (ty >= trows) return;
     const int R0 = blockIdx.x * (trows * NA_UNROLL);
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x
                 o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
             }
             *reinterpret_cast<float4*>(out + (size_t)r * C + 4 * cg) = o;
+            rsum[u] += (o.x + o.y) + (o.z + o.w);
             if (hi != nullptr) {
                 const float vv[4] = { o.x, o.y, o.z, o.w };
                 __align__(8) __nv_bfloat16 h[4], l[4];
@@ -180,6 +184,17 @@ __global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x
                 *reinterpret_cast<uint2*>(hi + (size_t)r * lds + 4 * cg) = *reinterpret_cast<const uint2*>(h);
                 *reinterpret_cast<uint2*>(lo + (size_t)r * lds + 4 * cg) = *reinterpret_cast<const uint2*>(l);
             }
+        }
+    }
+    // (row sum > 0) flags for the KPConv neighbour count (models/blocks.py:369-370): a row lives in tcols <= 32
+    // consecutive lanes of one warp in this mode, so a shuffle reduction finishes the sum deterministically
+    if (rowflag != nullptr) {
+#pragma unroll
+        for (int u = 0; u < NA_UNROLL; u++) {
+            float v = rsum[u];
+            for (int o = tcols >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int r = R0 + ty + u * trows;
+            if (tx == 0 && r < n) rowflag[r] = v > 0.f ? 1 : 0;
         }
     }
 }
@@ -262,20 +277,24 @@ int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
 
 int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
                  const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
-                 int32_t split_ld, cudaStream_t st)
+                 int32_t split_ld, uint8_t* rowflag, cudaStream_t st)
 {
     if (n == 0) return PCRCG_OK;
     PCRCG_REQUIRE(split_hi == nullptr || (split_lo != nullptr && split_ld % 8 == 0 && split_ld >= C), "norm_act: bad split geometry");
     ProfScope prof(PC_NORM, st, 1);
     if (C % 4 == 0 && n < (1ll << 31) && g_norm_v4) {
         const int c4 = C / 4;
-        const int tcols = c4 < 256 ? c4 : 256, trows = 256 / tcols;
+        // power-of-two column-group counts only in flag mode (shuffle reduction inside tcols lanes)
+        const bool flag_ok = rowflag != nullptr && (c4 & (c4 - 1)) == 0;
+        const int tcols = flag_ok ? (c4 < 32 ? c4 : 32) : (c4 < 256 ? c4 : 256), trows = 256 / tcols;
+        PCRCG_REQUIRE(rowflag == nullptr || flag_ok, "norm_act: row flags need a power-of-two channel count");
         k_norm_act_v4<<<(unsigned)cdiv64(n, trows * NA_UNROLL), 256, 0, st>>>(x, (int)n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd,
                                                                            slope, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo,
-                                                                           split_ld, tcols, trows);
+                                                                           split_ld, tcols, trows, rowflag);
         PCRCG_CUDA(cudaGetLastError());
         return PCRCG_OK;
     }
+    PCRCG_REQUIRE(rowflag == nullptr, "norm_act: row flags need C % 4 == 0");
     long long tot = (long long)n * ((C + 3) / 4);
     k_norm_act<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, mean, rstd, sc, C, sc_mean, sc_rstd, slope,
                                                           out, C, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, split_ld);

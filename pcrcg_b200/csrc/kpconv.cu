@@ -761,7 +761,7 @@ size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* idx, int idx_is_i64, int32_t H,
                        int32_t idx_stride, const float* x, int32_t cin, const float* kpts, int32_t K, float kp_extent,
                        const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                       const void* x_hi, const void* x_lo, int32_t ldxs)
+                       const void* x_hi, const void* x_lo, int32_t ldxs, const uint8_t* rowflag_in)
 {
     PCRCG_REQUIRE(K >= 1 && K <= KP_MAX - 1, "kpconv: kernel_size must be in [1,15]");
     PCRCG_REQUIRE(cin >= 1 && cout >= 1 && cout <= 2048 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
@@ -776,15 +776,16 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     Workspace W(ws, ws_bytes);
     float* wf_buf[2] = { W.take<float>((size_t)chunk * ldk), W.take<float>((size_t)chunk * ldk) };
     float* inv_cnt = W.take<float>((size_t)nq);
-    uint8_t* rowflag = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
+    uint8_t* rowflag_ws = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
+    const uint8_t* rowflag = rowflag_in != nullptr ? rowflag_in : rowflag_ws;
     __nv_bfloat16* b_hi = (__nv_bfloat16*)W.take<float>((size_t)cout * ldk);
     __nv_bfloat16* b_lo = b_hi + (size_t)cout * ldk;
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
     const float inv_extent = 1.0f / kp_extent;
     {
         ProfScope prof(PC_KPCONV_AGG, st, 1);
-        if (ns > 0) {
-            k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag);
+        if (ns > 0 && rowflag_in == nullptr) {
+            k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag_ws);
             PCRCG_CUDA(cudaGetLastError());
         }
     }

@@ -121,8 +121,10 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
         sp = getattr(x, "_pcrcg_split", None)
         if sp is not None and not _force_simt:
             hi, lo, ld = sp
+            rp = getattr(x, "_pcrcg_rowpos", None)
             check(L.pcrcg_kpconv_forward_split_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
-                                                   x.data_ptr(), hi.data_ptr(), lo.data_ptr(), ld, cin, kernel_points.data_ptr(), K,
+                                                   x.data_ptr(), hi.data_ptr(), lo.data_ptr(), ld,
+                                                   rp.data_ptr() if rp is not None else None, cin, kernel_points.data_ptr(), K,
                                                    float(KP_extent), weights.data_ptr(), cout, out.data_ptr(), ws.data_ptr(),
                                                    ws.numel(), _stream()))
         else:
@@ -193,7 +195,8 @@ def column_stats(x, segments=None, eps=1e-5):
     return mean, rstd, seg
 
 
-def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5, emit_split=False):
+def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5, emit_split=False,
+                      emit_rowpos=False):
     """act(IN(x) + [IN](shortcut)) with act = LeakyReLU(slope) or identity (slope=None).
     models/blocks.py:456-463 (+ :501, :590, :662, :678).  emit_split: also write the bf16 (hi, lo)
     planes of the result (attached as ``out._pcrcg_split``) for a following :func:`linear`."""
@@ -209,12 +212,18 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
     out = torch.empty_like(x)
     p = lambda t: t.data_ptr() if t is not None else None
     sp = _split_planes(n, c, x.device) if (emit_split and c % 8 == 0 and not _force_simt) else None
+    rp = None
+    if emit_rowpos and sp is not None and c % 4 == 0 and ((c // 4) & (c // 4 - 1)) == 0:
+        rp = torch.empty(n, dtype=torch.uint8, device=x.device)       # (row sum > 0) for the KPConv neighbour count
     with torch.cuda.device(x.device):
         check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
                                        p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), out.data_ptr(),
-                                       sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0, _stream()))
+                                       sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0,
+                                       rp.data_ptr() if rp is not None else None, _stream()))
     if sp is not None:
         out._pcrcg_split = sp
+    if rp is not None:
+        out._pcrcg_rowpos = rp
     return out
 
 
@@ -226,7 +235,7 @@ def add_act(x, shortcut, slope):
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), 1, None, None, shortcut.data_ptr(), None, None,
-                                       float(slope), out.data_ptr(), None, None, 0, _stream()))
+                                       float(slope), out.data_ptr(), None, None, 0, None, _stream()))
     return out
 
 
