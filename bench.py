@@ -393,10 +393,12 @@ def main():
                     "traffic": traffic, "peak_source": peak_src}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.simt else "f32 (contraction: see config.contraction)", "data": "synthetic",
+                "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl_name, "pairs_per_step_per_gpu": P, "points_per_level": Nlev, "limits": list(limits),
                            "first_feats_dim": cfg.first_feats_dim, "l2": "256 MiB flush write between timed iterations",
-                           "contraction": "fp32 CUDA cores" if args.simt else "tcgen05 where shapes allow, else fp32 CUDA cores",
+                           "contraction": "fp32 CUDA cores" if args.simt else
+                           "fp32 operands split into bf16 hi/lo: tcgen05 bf16x3 contraction + mma.sync bf16x3/3xTF32 aggregation, fp32 accumulate "
+                           "(fp32 CUDA cores for ragged shapes such as Cin=1)",
                            "parallelism": f"pairs sharded by rank x{world}, no collective on the path"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes + lens_np.nbytes),
