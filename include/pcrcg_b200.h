@@ -130,6 +130,11 @@ int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
                        float* out, void* split_hi, void* split_lo, int32_t split_ld, uint8_t* row_positive,
                        pcrcg_stream_t stream);
 
+/* Descriptor head (models/architectures.py:572-582, "next" row of the scope table): x [n, F+2] ->
+ * feats [n,F] = x[:, :F] / max(|x[:, :F]|_2, 1e-12); overlap / saliency [n] = clamp(sigmoid(x[:, F | F+1]), 0, 1), NaN/Inf -> 0 */
+int pcrcg_descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency,
+                              pcrcg_stream_t stream);
+
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,
                        int32_t idx_stride, float* out, pcrcg_stream_t stream);

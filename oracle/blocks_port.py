@@ -142,3 +142,21 @@ def encoder_blocks_from_state_dict(sd, architecture=INDOOR_ARCHITECTURE, first_s
             layer += 1
             r *= 2
     return blocks
+
+
+def decoder(x, skips, batch, unary_weights, final_feats_dim):
+    """models/architectures.py:567-582 for the indoor / kitti architecture tail
+    (nearest_upsample, unary, nearest_upsample, unary, nearest_upsample, last_unary).
+    unary_weights: [W_unary_1, W_unary_2, W_last]  (nn.Linear weights [out, in])."""
+    skips = list(skips)
+    n_up = len(unary_weights)
+    for i, W in enumerate(unary_weights):
+        layer = n_up - i                                   # upsample from `layer` to `layer - 1`
+        x = closest_pool(x, batch["upsamples"][layer - 1])  # NearestUpsampleBlock, models/blocks.py:704-705
+        x = torch.cat([x, skips.pop()], dim=1)
+        x = unary(x, W) if i < n_up - 1 else x @ W.t()      # UnaryBlock / LastUnaryBlock
+    feats = F.normalize(x[:, :final_feats_dim], p=2, dim=1)
+    so = torch.clamp(torch.sigmoid(x[:, final_feats_dim]), 0, 1)
+    ss = torch.clamp(torch.sigmoid(x[:, final_feats_dim + 1]), 0, 1)
+    fix = lambda t: torch.where(torch.isfinite(t), t, torch.zeros_like(t))
+    return feats, fix(so), fix(ss), x

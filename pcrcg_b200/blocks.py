@@ -293,3 +293,56 @@ class KPEncoder(nn.Module):
                 skips.append(x)
             x = block_op(x, batch)
         return (x, skips) if return_skips else x
+
+
+class KPDecoder(nn.Module):
+    """The decoder tail of KPFCNN (construction models/architectures.py:114-153, loop :567-582):
+    nearest_upsample -> concat skip -> unary ... -> last_unary, then the descriptor head.  Module names equal the
+    reference's (``decoder_blocks.<i>.mlp.weight``), so ``KPFCNN.state_dict()`` entries load unchanged.  The
+    bottleneck GNN between encoder and decoder stays with the reference (out of the hot-path scope)."""
+
+    def __init__(self, config, encoder, gnn_feats_dim):
+        super().__init__()
+        arch = config.architecture
+        start_i = next(i for i, b in enumerate(arch) if "upsample" in b)
+        n_strided = sum(1 for b in arch[:start_i] if "pool" in b or "strided" in b)
+        layer = n_strided
+        r = config.first_subsampling_dl * config.conv_radius * (2 ** n_strided)
+        in_dim, out_dim = encoder.out_dim, gnn_feats_dim + 2
+        self.final_feats_dim = config.final_feats_dim
+        self.decoder_blocks = nn.ModuleList()
+        self.decoder_concats, self.block_layers = [], []
+        for block_i, block in enumerate(arch[start_i:]):
+            if block_i > 0 and "upsample" in arch[start_i + block_i - 1]:
+                in_dim += encoder.encoder_skip_dims[layer]
+                self.decoder_concats.append(block_i)
+            self.decoder_blocks.append(block_decider(block, r, in_dim, out_dim, layer, config))
+            self.block_layers.append(layer)
+            in_dim = out_dim
+            if "upsample" in block:
+                layer -= 1
+                r *= 0.5
+                out_dim = out_dim // 2
+
+    def load_reference(self, state_dict, prefix="decoder_blocks."):
+        own = self.state_dict()
+        for k in own:
+            src = prefix + k[len("decoder_blocks."):]
+            if src not in state_dict:
+                raise KeyError(f"missing {src} in reference state_dict")
+            own[k].copy_(torch.as_tensor(state_dict[src]))
+        return self
+
+    @torch.no_grad()
+    def forward(self, x, skips, batch):
+        """x [N_coarse, gnn_feats_dim + 2] (scores_c_raw, scores_saliency, feats_gnn_raw), skips = the encoder's skip list.
+        -> (feats_f [N0, final_feats_dim], scores_overlap [N0], scores_saliency [N0])"""
+        skips = list(skips)
+        for block_i, block_op in enumerate(self.decoder_blocks):
+            if block_i in self.decoder_concats:
+                x = torch.cat([x, skips.pop()], dim=1)
+            if isinstance(block_op, UnaryBlock):
+                x = block_op(x, batch, segments=_segments(batch, self.block_layers[block_i]))
+            else:
+                x = block_op(x, batch)
+        return ops.descriptor_head(x, self.final_feats_dim)

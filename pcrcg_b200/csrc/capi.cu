@@ -66,6 +66,7 @@ int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float,
 int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
                  const float*, float, float*, void*, void*, int32_t, uint8_t*, cudaStream_t);
 int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
+int descriptor_head_dev(const float*, int64_t, int32_t, float*, float*, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
 size_t projection_ws_bytes(int64_t n);
@@ -267,6 +268,11 @@ int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
 {
     return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld, row_positive,
                         (cudaStream_t)stream);
+}
+
+int pcrcg_descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency, pcrcg_stream_t stream)
+{
+    return descriptor_head_dev(x, n, F, feats, overlap, saliency, (cudaStream_t)stream);
 }
 
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H, int32_t idx_stride,

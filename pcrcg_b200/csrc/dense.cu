@@ -253,6 +253,29 @@ __global__ void __launch_bounds__(256) k_closest_pool(const float* __restrict__ 
     for (int c = lane; c < C; c += 32) out[(size_t)n * C + c] = ok ? __ldg(x + (size_t)j * ldx + c) : 0.f;
 }
 
+// Descriptor head of KPFCNN.forward (models/architectures.py:572-582): L2-normalised features (F.normalize, eps 1e-12)
+// and the two sigmoid scores, clamped to [0,1], NaN / Inf -> 0 (regular_score, :176-179).  One warp per row.
+__global__ void __launch_bounds__(256) k_descriptor_head(const float* __restrict__ x, int n, int F, float* __restrict__ feats,
+                                                         float* __restrict__ overlap, float* __restrict__ saliency)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float* row = x + (size_t)r * (F + 2);
+    float ss = 0.f;
+    for (int c = lane; c < F; c += 32) { float v = row[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < F; c += 32) feats[(size_t)r * F + c] = row[c] * inv;
+    if (lane < 2) {
+        float v = 1.0f / (1.0f + expf(-row[F + lane]));
+        v = fminf(fmaxf(v, 0.f), 1.f);
+        if (!(v == v) || isinf(v)) v = 0.f;
+        (lane == 0 ? overlap : saliency)[r] = v;
+    }
+}
+
 static int g_norm_v4 = 1;
 void dense_set_norm_v4(int v) { g_norm_v4 = v; }
 
@@ -298,6 +321,16 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
     long long tot = (long long)n * ((C + 3) / 4);
     k_norm_act<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(x, C, (int)n, C, seg_starts, nseg, mean, rstd, sc, C, sc_mean, sc_rstd, slope,
                                                           out, C, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, split_ld);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+int descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency, cudaStream_t st)
+{
+    PCRCG_REQUIRE(F >= 1 && n >= 0 && n < (1ll << 31), "descriptor head: bad dimensions");
+    if (n == 0) return PCRCG_OK;
+    ProfScope prof(PC_NORM, st, 1);
+    k_descriptor_head<<<(unsigned)cdiv64(n, 8), 256, 0, st>>>(x, (int)n, F, feats, overlap, saliency);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

@@ -263,6 +263,22 @@ def closest_pool(x, inds):
     return out
 
 
+def descriptor_head(x, final_feats_dim):
+    """models/architectures.py:572-582: -> (feats_f [N,F] L2-normalised, scores_overlap [N], scores_saliency [N])"""
+    _need_cuda(x)
+    x = _f32c(x)
+    n, c = x.shape
+    F = int(final_feats_dim)
+    if c != F + 2:
+        raise RuntimeError("descriptor_head: expected final_feats_dim + 2 columns")
+    feats = torch.empty((n, F), dtype=torch.float32, device=x.device)
+    ov = torch.empty(n, dtype=torch.float32, device=x.device)
+    sa = torch.empty(n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_descriptor_head_dev(x.data_ptr(), n, F, feats.data_ptr(), ov.data_ptr(), sa.data_ptr(), _stream()))
+    return feats, ov, sa
+
+
 def force_simt_contraction(on):
     """True: fp32 CUDA-core contraction (parity anchor); False: tcgen05 tensor cores where shapes allow."""
     global _force_simt

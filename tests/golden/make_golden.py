@@ -184,6 +184,42 @@ def main():
     np.savez_compressed(f"{OUT}/encoder_ref.npz", **ge)
     print("encoder out", x.shape)
 
+    # ---- decoder tail: models/architectures.py:567-582 ------------------
+    import torch.nn.functional as F
+    cfg = indoor_cfg(first_feats_dim=32)
+    cfg.gnn_feats_dim = 64
+    torch.manual_seed(2); np.random.seed(2)
+    net = KPFCNN(cfg).eval()
+    gd = {}
+    with torch.no_grad():
+        x = torch.ones(len(pts), 1)
+        skip_x = []
+        for bi, blk in enumerate(net.encoder_blocks):
+            if bi in net.encoder_skips:
+                skip_x.append(x)
+            x = blk(x, batch)
+        for i, t in enumerate(skip_x):
+            gd[f"skip_{i}"] = t.numpy()
+        xb = torch.randn(x.shape[0], cfg.gnn_feats_dim + 2)          # [scores_c_raw, scores_saliency, feats_gnn_raw]
+        gd["bottleneck_x"] = xb.numpy()
+        x = xb
+        skips = list(skip_x)
+        for bi, blk in enumerate(net.decoder_blocks):
+            if bi in net.decoder_concats:
+                x = torch.cat([x, skips.pop()], dim=1)
+            x = blk(x, batch)
+        gd["decoder_out"] = x.numpy()
+        feats_f = x[:, :cfg.final_feats_dim]
+        so = torch.clamp(torch.sigmoid(x[:, cfg.final_feats_dim].view(-1)), min=0, max=1)
+        ss = torch.clamp(torch.sigmoid(x[:, cfg.final_feats_dim + 1].view(-1)), min=0, max=1)
+        gd["feats_f"] = F.normalize(feats_f, p=2, dim=1).numpy()
+        gd["scores_overlap"], gd["scores_saliency"] = net.regular_score(so).numpy(), net.regular_score(ss).numpy()
+    for k, v in net.decoder_blocks.state_dict().items():
+        gd["sd_" + k] = v.numpy()
+    gd["encoder_skip_dims"] = np.array(net.encoder_skip_dims)
+    np.savez_compressed(f"{OUT}/decoder_ref.npz", **gd)
+    print("decoder out", x.shape)
+
     # ---- projection --------------------------------------------------------------------------
     from projection import Projection
     gp = {}

@@ -158,3 +158,43 @@ def test_kpconv_bf16_plane_path_vs_port(cin, cout, H, contraction_path):
     out = ops.kpconv_forward(_d(pts), _d(pts), rows, x, kp.to(DEV), w.to(DEV), 0.05)
     assert _err(out, ref) < TOL
     assert _err(out, ref) < 1e-4      # the split schemes are fp32-class, far inside the tolerance
+
+
+def test_decoder_tail_vs_reference_golden(blk):
+    """nearest_upsample / unary / last_unary + descriptor head vs the reference's decoder."""
+    dec = np.load(os.path.join(G, "decoder_ref.npz"))
+    cfg = blocks.indoor_config(first_feats_dim=32)
+    enc = blocks.KPEncoder(cfg)
+    assert enc.encoder_skip_dims == dec["encoder_skip_dims"].tolist()
+    net = blocks.KPDecoder(cfg, enc, gnn_feats_dim=64).to(DEV)
+    net.load_reference({k[3:]: dec[k] for k in dec.files if k.startswith("sd_")}, prefix="")
+    P, nb, pools, ups = _geom(blk)
+    batch = dict(points=P, neighbors=nb, pools=pools, upsamples=ups)
+    skips = [_d(dec[f"skip_{i}"]) for i in range(3)]
+    feats, so, ss = net(_d(dec["bottleneck_x"]), skips[:3], batch)
+    assert feats.shape == dec["feats_f"].shape
+    assert _err(feats, dec["feats_f"]) < TOL and _err(so, dec["scores_overlap"]) < TOL and _err(ss, dec["scores_saliency"]) < TOL
+
+
+def test_calibrate_neighbors_equals_reference_rule():
+    """calibrate_neighbors on the GPU == the reference rule (datasets/dataloader.py:402-434)
+    evaluated with the CPU oracle's neighbour counts on the same pairs."""
+    import oracle
+    P = oracle.port()
+    cfg = blocks.indoor_config()
+    pairs = [synthetic.match3d_pair(40 + s, n_target=2500)[:2] for s in range(3)]
+    got = dataloader.calibrate_neighbors(iter(pairs), cfg, samples_threshold=10 ** 9, device=DEV)
+    hist_n = int(np.ceil(4 / 3 * np.pi * (cfg.deform_radius + 1) ** 3))
+    hists = np.zeros((4, hist_n), np.int64)
+    for src, tgt in pairs:
+        pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+        r = cfg.first_subsampling_dl * cfg.conv_radius
+        for l in range(4):
+            c, _ = P.radius_counts(pts, pts, lens, lens, r)
+            hists[l] += np.bincount(np.minimum(c, hist_n), minlength=hist_n)[:hist_n]
+            if l < 3:
+                pts, lens = P.subsample_batch(pts, lens, 2 * r / cfg.conv_radius)
+            r *= 2
+    cs = np.cumsum(hists.T, axis=0)
+    want = np.sum(cs < 0.8 * cs[hist_n - 1, :], axis=0)
+    assert got.tolist() == want.tolist()

@@ -185,3 +185,13 @@ def test_projection_port_vs_reference_golden():
         views.append((g[f"v{vi}_feature2d"], g[f"v{vi}_valid_map"], i2, i3))
     x = pp.scatter_image_features(len(g["points"]), [views[1], views[0]])
     assert np.array_equal(x, g["x_out"])
+
+
+def test_decoder_port_vs_reference_golden(blk):
+    dec = np.load(os.path.join(G, "decoder_ref.npz"))
+    batch = {k: [_t(blk[f"{k}_{l}"]) for l in range(4)] for k in ("points", "upsamples")}
+    skips = [_t(dec[f"skip_{i}"]) for i in range(3)]
+    Ws = [_t(dec["sd_1.mlp.weight"]), _t(dec["sd_3.mlp.weight"]), _t(dec["sd_5.mlp.weight"])]
+    feats, so, ss, raw = bp.decoder(_t(dec["bottleneck_x"]), skips[:3], batch, Ws, 32)
+    assert _close(raw, dec["decoder_out"], 1e-4) and _close(feats, dec["feats_f"], 1e-4)
+    assert _close(so, dec["scores_overlap"], 1e-4) and _close(ss, dec["scores_saliency"], 1e-4)
