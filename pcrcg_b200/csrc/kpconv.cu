@@ -562,16 +562,18 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
     if (n >= nq) return;
     uint8_t* s_hi = smem_b + (size_t)w * AB_WARP_BYTES;
     uint8_t* s_lo = s_hi + AB_ROWS * AB_PITCH;
-    float* s_xyz = reinterpret_cast<float*>(s_lo + AB_ROWS * AB_PITCH);      // [row][x,y,z,valid]
+    float* s_xyz = reinterpret_cast<float*>(s_lo + AB_ROWS * AB_PITCH);      // [row][x', y', z', |p'|^2 or -1]  (p' = p - q)
     const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(s_hi), a_lo = (uint32_t)__cvta_generic_to_shared(s_lo);
     const int g = lane >> 2, t = lane & 3;
     const int c0 = blockIdx.y * 64;
 
     const float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
+    // |p' - k|^2 = |p'|^2 + |k|^2 - 2 p'.k : the kernel-point terms are per-lane constants (kernel points g and g+8)
     const bool k1ok = g + 8 < K, k0ok = g < K;
     const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
-    const float k0x = kpts[3 * ka] + qx, k0y = kpts[3 * ka + 1] + qy, k0z = kpts[3 * ka + 2] + qz;
-    const float k1x = kpts[3 * kb] + qx, k1y = kpts[3 * kb + 1] + qy, k1z = kpts[3 * kb + 2] + qz;
+    const float k0x = -2.f * kpts[3 * ka], k0y = -2.f * kpts[3 * ka + 1], k0z = -2.f * kpts[3 * ka + 2];
+    const float k1x = -2.f * kpts[3 * kb], k1y = -2.f * kpts[3 * kb + 1], k1z = -2.f * kpts[3 * kb + 2];
+    const float k0n = 0.25f * (k0x * k0x + k0y * k0y + k0z * k0z), k1n = 0.25f * (k1x * k1x + k1y * k1y + k1z * k1z);
 
     float acc[8][4];
 #pragma unroll
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
     // staging: lanes 0..7 copy the 8 x 16-byte chunks of a hi row, 8..15 of the lo row; lanes 16..31 the next neighbour
     const int chunk = lane & 7, plane = (lane >> 3) & 1, rsel = lane >> 4;
     const __nv_bfloat16* xp = (plane ? x_lo : x_hi) + c0 + chunk * 8;
-    uint8_t* sp_dst = (plane ? s_lo : s_hi) + chunk * 16;
+    const uint32_t dst0 = (plane ? a_lo : a_hi) + (uint32_t)(chunk * 16 + rsel * AB_PITCH);
     // ldmatrix lane addressing: matrix m = lane>>3 -> (k half = m&1, n-tile offset = m>>1), row = lane&7
     const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
 
@@ -589,20 +591,26 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
         int ja = ns;
         if (h0 + lane < H) { long long v = (long long)row[h0 + lane]; ja = (v >= 0 && v < ns) ? (int)v : ns; }
         const bool va = ja < ns;
-        {
-            float* d = s_xyz + lane * 4;
-            const float* sp = s_pts + 3 * (size_t)(va ? ja : 0);
-            cp_async4(d, sp, va); cp_async4(d + 1, sp + 1, va); cp_async4(d + 2, sp + 2, va);
-            d[3] = va ? 1.f : 0.f;
-        }
-#pragma unroll 4
+        // feature planes: 16 unrolled cp.async of 16 bytes per lane (2 neighbour rows per step)
+#pragma unroll
         for (int r = 0; r < AB_ROWS; r += 2) {
-            const int rr = r + rsel;
-            const int j = __shfl_sync(0xffffffffu, ja, rr);
+            const int j = __shfl_sync(0xffffffffu, ja, r + rsel);
             const bool v = j < ns;
-            cp_async16(sp_dst + rr * AB_PITCH, xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs), v);
+            const void* src = xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs);
+            const int sz = v ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(r * AB_PITCH)), "l"(src), "r"(sz) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        // coordinates relative to the query, squared norm (or -1 = shadow) -- one neighbour per lane
+        {
+            float px = 0.f, py = 0.f, pz = 0.f, pn = -1.f;
+            if (va) {
+                const float* sp = s_pts + 3 * (size_t)ja;
+                px = sp[0] - qx; py = sp[1] - qy; pz = sp[2] - qz;
+                pn = fmaf(px, px, fmaf(py, py, pz * pz));
+            }
+            *reinterpret_cast<float4*>(s_xyz + lane * 4) = make_float4(px, py, pz, pn);
+        }
         if (blockIdx.y == 0) cnt += __popc(__ballot_sync(0xffffffffu, va && rowflag[ja] != 0));
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -616,9 +624,13 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
             for (int e = 0; e < 4; e++) {
                 const int rn = 16 * s + 2 * t + (e & 1) + (e >> 1) * 8;
                 const float4 p = *reinterpret_cast<const float4*>(s_xyz + rn * 4);
-                const float sa[3] = { p.x, p.y, p.z };
-                wv[0][e] = (p.w != 0.f && k0ok) ? influence(sa, k0x, k0y, k0z, inv_extent) : 0.f;
-                wv[1][e] = (p.w != 0.f && k1ok) ? influence(sa, k1x, k1y, k1z, inv_extent) : 0.f;
+                const bool ok = p.w >= 0.f;
+                const float d0 = fmaxf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))), 1e-30f);
+                const float d1 = fmaxf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))), 1e-30f);
+                const float w0 = fmaxf(0.f, fmaf(-d0 * rsqrtf(d0), inv_extent, 1.f));
+                const float w1 = fmaxf(0.f, fmaf(-d1 * rsqrtf(d1), inv_extent, 1.f));
+                wv[0][e] = (ok && k0ok) ? w0 : 0.f;
+                wv[1][e] = (ok && k1ok) ? w1 : 0.f;
             }
             uint32_t ahi[4], alo[4];
             ahi[0] = pack_split(wv[0][0], wv[0][1], alo[0]);     // row g   , k 2t..2t+1
@@ -632,10 +644,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
                 ldmatrix_x4_trans(bh, a_hi + sbase + np * 32);
                 ldmatrix_x4_trans(bl, a_lo + sbase + np * 32);
                 mma_bf16(acc[2 * np], alo, bh[0], bh[1]);
-                mma_bf16(acc[2 * np], ahi, bl[0], bl[1]);
-                mma_bf16(acc[2 * np], ahi, bh[0], bh[1]);
                 mma_bf16(acc[2 * np + 1], alo, bh[2], bh[3]);
+                mma_bf16(acc[2 * np], ahi, bl[0], bl[1]);
                 mma_bf16(acc[2 * np + 1], ahi, bl[2], bl[3]);
+                mma_bf16(acc[2 * np], ahi, bh[0], bh[1]);
                 mma_bf16(acc[2 * np + 1], ahi, bh[2], bh[3]);
             }
         }
@@ -659,11 +671,12 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
         __syncwarp();
         // 16 rows x 128 bytes per plane: 8 lanes per row, 4 rows per instruction
         const int rl = lane >> 3, cl = lane & 7;
+        const size_t ebase = (size_t)n * ldk + c0 + cl * 8;
 #pragma unroll
         for (int r0 = 0; r0 < 16; r0 += 4) {
             const int kp = r0 + rl;
             if (kp < K) {
-                const size_t e = (size_t)n * ldk + (size_t)kp * cin + c0 + cl * 8;
+                const size_t e = ebase + (size_t)kp * cin;
                 *reinterpret_cast<uint4*>(wf_hi + e) = *reinterpret_cast<const uint4*>(s_hi + kp * AB_PITCH + cl * 16);
                 *reinterpret_cast<uint4*>(wf_lo + e) = *reinterpret_cast<const uint4*>(s_lo + kp * AB_PITCH + cl * 16);
             }
