@@ -531,6 +531,12 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
 {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -543,10 +549,12 @@ __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t
 // packs (lo half = a, hi half = b) as bf16x2 and returns the residuals
 __device__ __forceinline__ uint32_t pack_split(float a, float b, uint32_t& lo_packed)
 {
-    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-    lo_packed = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                    // one packed conversion (.x = a in the low half)
+    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hu << 16), hb = __uint_as_float(hu & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo_packed = *reinterpret_cast<const uint32_t*>(&l);
+    return hu;
 }
 
 template <typename IdxT>
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
     if (n >= nq) return;
     uint8_t* s_hi = smem_b + (size_t)w * AB_WARP_BYTES;
     uint8_t* s_lo = s_hi + AB_ROWS * AB_PITCH;
-    float* s_xyz = reinterpret_cast<float*>(s_lo + AB_ROWS * AB_PITCH);      // [row][x', y', z', |p'|^2 or -1]  (p' = p - q)
+    float* s_xyz = reinterpret_cast<float*>(s_lo + AB_ROWS * AB_PITCH);      // [row][x', y', z', |p'|^2 or 1e30 for a shadow]  (p' = p - q)
     const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(s_hi), a_lo = (uint32_t)__cvta_generic_to_shared(s_lo);
     const int g = lane >> 2, t = lane & 3;
     const int c0 = blockIdx.y * 64;
@@ -573,7 +581,9 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
     const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
     const float k0x = -2.f * kpts[3 * ka], k0y = -2.f * kpts[3 * ka + 1], k0z = -2.f * kpts[3 * ka + 2];
     const float k1x = -2.f * kpts[3 * kb], k1y = -2.f * kpts[3 * kb + 1], k1z = -2.f * kpts[3 * kb + 2];
-    const float k0n = 0.25f * (k0x * k0x + k0y * k0y + k0z * k0z), k1n = 0.25f * (k1x * k1x + k1y * k1y + k1z * k1z);
+    // a missing kernel point (k >= K) or a shadow neighbour gets a huge squared distance -> influence exactly 0
+    const float k0n = k0ok ? 0.25f * (k0x * k0x + k0y * k0y + k0z * k0z) : 1e30f;
+    const float k1n = k1ok ? 0.25f * (k1x * k1x + k1y * k1y + k1z * k1z) : 1e30f;
 
     float acc[8][4];
 #pragma unroll
@@ -603,7 +613,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
         asm volatile("cp.async.commit_group;" ::: "memory");
         // coordinates relative to the query, squared norm (or -1 = shadow) -- one neighbour per lane
         {
-            float px = 0.f, py = 0.f, pz = 0.f, pn = -1.f;
+            float px = 0.f, py = 0.f, pz = 0.f, pn = 1e30f;
             if (va) {
                 const float* sp = s_pts + 3 * (size_t)ja;
                 px = sp[0] - qx; py = sp[1] - qy; pz = sp[2] - qz;
@@ -624,13 +634,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
             for (int e = 0; e < 4; e++) {
                 const int rn = 16 * s + 2 * t + (e & 1) + (e >> 1) * 8;
                 const float4 p = *reinterpret_cast<const float4*>(s_xyz + rn * 4);
-                const bool ok = p.w >= 0.f;
-                const float d0 = fmaxf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))), 1e-30f);
-                const float d1 = fmaxf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))), 1e-30f);
-                const float w0 = fmaxf(0.f, fmaf(-d0 * rsqrtf(d0), inv_extent, 1.f));
-                const float w1 = fmaxf(0.f, fmaf(-d1 * rsqrtf(d1), inv_extent, 1.f));
-                wv[0][e] = (ok && k0ok) ? w0 : 0.f;
-                wv[1][e] = (ok && k1ok) ? w1 : 0.f;
+                const float d0 = fmaxf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))), 0.f);
+                const float d1 = fmaxf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))), 0.f);
+                wv[0][e] = fmaxf(0.f, fmaf(-sqrt_approx(d0), inv_extent, 1.f));
+                wv[1][e] = fmaxf(0.f, fmaf(-sqrt_approx(d1), inv_extent, 1.f));
             }
             uint32_t ahi[4], alo[4];
             ahi[0] = pack_split(wv[0][0], wv[0][1], alo[0]);     // row g   , k 2t..2t+1
