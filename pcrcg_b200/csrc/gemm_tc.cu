@@ -336,11 +336,8 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
     PCRCG_TRY(make_map(&ma_lo, a_lo, M, K, ldk, TC_BM));
     PCRCG_TRY(make_map(&mb_hi, b_hi, N, K, ldk, BN));
     PCRCG_TRY(make_map(&mb_lo, b_lo, N, K, ldk, BN));
-    static bool attr_set = false;
-    if (!attr_set) {
-        PCRCG_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    // per device (function attributes live in the context): cheap enough to set on every launch
+    PCRCG_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int n_tiles_n = (int)cdiv64(N, BN);
     const long long total = cdiv64(M, TC_BM) * n_tiles_n;
     PCRCG_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
@@ -350,18 +347,18 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
     return PCRCG_OK;
 }
 
-static bool g_pool_ready = false;
+static bool g_pool_ready[64] = { false };       // per device
 
 int pool_setup()
 {
-    if (g_pool_ready) return PCRCG_OK;
     int dev = 0;
-    cudaMemPool_t pool;
     PCRCG_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && g_pool_ready[dev]) return PCRCG_OK;
+    cudaMemPool_t pool;
     PCRCG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = ~0ull;
     PCRCG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    g_pool_ready = true;
+    if (dev >= 0 && dev < 64) g_pool_ready[dev] = true;
     return PCRCG_OK;
 }
 

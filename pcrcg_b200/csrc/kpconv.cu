@@ -717,11 +717,7 @@ static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, co
 #define PCRCG_AGG_MMA(NT_) k_kpconv_aggregate_mma<IdxT, NT_, SPLIT><<<dim3(gx, (unsigned)(cin / (8 * NT_))), block, 0, st>>>( \
         q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt)
         if (cin % 64 == 0) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                PCRCG_CUDA(cudaFuncSetAttribute(k_kpconv_aggregate_mma64<IdxT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM));
-                attr_done = true;
-            }
+            PCRCG_CUDA(cudaFuncSetAttribute(k_kpconv_aggregate_mma64<IdxT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM));
             k_kpconv_aggregate_mma64<IdxT, SPLIT><<<dim3((unsigned)cdiv64(nq, A64_WARPS), (unsigned)(cin / 64)), A64_WARPS * 32, A64_SMEM, st>>>(
                 q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, ldx, rowflag, kpts, K, inv_extent, wf, wf_hi, wf_lo, ldk, inv_cnt);
         }
