@@ -95,6 +95,17 @@ int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* 
                                    float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
                                    pcrcg_stream_t stream);
 
+/* Same, and the contraction epilogue ALSO accumulates the InstanceNorm statistics of `out` (the BatchNormBlock that
+ * follows every KPConv, models/blocks.py:590,662): stats_acc [nseg][2][cout] fp64, zeroed by the caller, receives per
+ * (segment, column) the sum and the sum of squares; pcrcg_colstats_final_dev turns them into mean / rstd.  Saves the
+ * statistics pass over `out`.  Tensor-core path only (cout % 16 == 0); x_hi / x_lo may be NULL. */
+int pcrcg_kpconv_forward_stats_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
+                                   int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi,
+                                   const void* x_lo, int32_t ldxs, const uint8_t* row_positive, int32_t cin,
+                                   const float* kernel_points, int32_t K, float KP_extent, const float* weights, int32_t cout,
+                                   float* out, void* ws, size_t ws_bytes, const int32_t* seg_starts, int32_t nseg,
+                                   double* stats_acc, pcrcg_stream_t stream);
+
 /* Dense contraction C[M,N] = A[M,K] * B (* row_scale[m] if not NULL).  B is [K,N] (b_is_nk = 0) or
  * [N,K] (b_is_nk = 1, nn.Linear.weight of models/blocks.py:490).  Row-major, leading dims in elements. */
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc,
@@ -106,6 +117,11 @@ int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols
                          pcrcg_stream_t stream);
 int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C,
                           int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
+/* Same with the column statistics of C accumulated by the epilogue (see pcrcg_kpconv_forward_stats_dev):
+ * UnaryBlock = Linear -> InstanceNorm (models/blocks.py:497-499) without a statistics pass over C. */
+int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C,
+                                int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, const int32_t* seg_starts,
+                                int32_t nseg, double* stats_acc, pcrcg_stream_t stream);
 /* 1: force the fp32 CUDA-core contraction (parity anchor); 0: tcgen05 tensor-core path where shapes allow. */
 void pcrcg_gemm_force_simt(int32_t on);
 /* A/B switches for measurements: "contraction_simt", "aggregate_simt" (CUDA-core variants of the two KPConv stages),
@@ -125,6 +141,10 @@ int pcrcg_set_option(const char* name, int32_t value);
  * ------------------------------------------------------------------------------------------- */
 int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps,
                        float* mean, float* rstd, pcrcg_stream_t stream);
+/* stats_acc [nseg][2][C] fp64 (sum, sum of squares; from the *_stats_dev contractions) -> mean / rstd [nseg,C]
+ * (biased variance, models/blocks.py:448) */
+int pcrcg_colstats_final_dev(const double* stats_acc, const int32_t* seg_starts, int32_t nseg, int32_t C, float eps,
+                             float* mean, float* rstd, pcrcg_stream_t stream);
 int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
                        const float* rstd, const float* sc, const float* sc_mean, const float* sc_rstd, float slope,
                        float* out, void* split_hi, void* split_lo, int32_t split_ld, uint8_t* row_positive,

@@ -37,9 +37,12 @@ SIGNATURES = {
     "pcrcg_kpconv_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "pcrcg_kpconv_forward_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),
     "pcrcg_kpconv_forward_split_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),
+    "pcrcg_kpconv_forward_stats_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P, _I32, _P, _P]),
     "pcrcg_gemm_dev": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "pcrcg_split_bf16_dev": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _I32, _P]),
     "pcrcg_gemm_bf16x3_dev": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "pcrcg_gemm_bf16x3_stats_dev": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P]),
+    "pcrcg_colstats_final_dev": (C.c_int, [_P, _P, _I32, _I32, _F, _P, _P, _P]),
     "pcrcg_set_option": (C.c_int, [C.c_char_p, _I32]),
     "pcrcg_gemm_force_simt": (None, [_I32]),
     "pcrcg_colstats_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _F, _P, _P, _P]),

@@ -36,6 +36,11 @@ def max_pool(x, inds):
     return ops.max_pool(x, inds)
 
 
+def _stat_arg(segments):
+    """segments (None = one group) -> the stat_segments argument of the contractions"""
+    return True if segments is None else segments
+
+
 def _segments(batch, layer):
     seg = batch.get("pair_segments") if isinstance(batch, dict) else None
     return None if seg is None else seg[layer]
@@ -66,8 +71,10 @@ class KPConv(nn.Module):
         with torch.no_grad():
             self.kernel_points.copy_(torch.as_tensor(pts, dtype=torch.float32))
 
-    def forward(self, q_pts, s_pts, neighb_inds, x):
-        return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent)
+    def forward(self, q_pts, s_pts, neighb_inds, x, stat_segments=False):
+        """stat_segments (extension, default off = the reference signature): the row starts of the normalisation groups of
+        the BatchNormBlock that consumes the result; its statistics are then accumulated by the contraction epilogue."""
+        return ops.kpconv_forward(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent, stat_segments)
 
     def __repr__(self):
         return "KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})".format(
@@ -98,8 +105,8 @@ class _Linear(nn.Module):
         self.weight = Parameter(torch.empty(out_dim, in_dim, dtype=torch.float32), requires_grad=False)
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
 
-    def forward(self, x):
-        return ops.linear(x, self.weight)
+    def forward(self, x, stat_segments=False):
+        return ops.linear(x, self.weight, stat_segments)
 
 
 class UnaryBlock(nn.Module):
@@ -111,7 +118,8 @@ class UnaryBlock(nn.Module):
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
     def forward(self, x, batch=None, segments=None, emit_split=False, emit_rowpos=False):
-        return self.batch_norm(self.mlp(x), segments, None if self.no_relu else 0.1, emit_split=emit_split, emit_rowpos=emit_rowpos)
+        y = self.mlp(x, _stat_arg(segments) if self.use_bn else False)
+        return self.batch_norm(y, segments, None if self.no_relu else 0.1, emit_split=emit_split, emit_rowpos=emit_rowpos)
 
 
 class LastUnaryBlock(nn.Module):
@@ -145,8 +153,9 @@ class SimpleBlock(nn.Module):
 
     def forward(self, x, batch):
         q_pts, s_pts, inds, out_layer = _block_geometry(self.block_name, self.layer_ind, batch)
-        x = self.KPConv(q_pts, s_pts, inds, x)
-        return self.batch_norm(x, _segments(batch, out_layer), 0.1, emit_split=True)      # feeds the next block's unary1
+        seg = _segments(batch, out_layer)
+        x = self.KPConv(q_pts, s_pts, inds, x, _stat_arg(seg) if self.use_bn else False)
+        return self.batch_norm(x, seg, 0.1, emit_split=True)      # feeds the next block's unary1
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -170,12 +179,13 @@ class ResnetBottleneckBlock(nn.Module):
         seg_in, seg_out = _segments(batch, self.layer_ind), _segments(batch, out_layer)
         # unary1's output is gathered by the KPConv aggregation: emit its bf16 planes for the bf16x3 kernel
         x = self.unary1(features, segments=seg_in, emit_split=True, emit_rowpos=True) if isinstance(self.unary1, UnaryBlock) else features
-        x = self.KPConv(q_pts, s_pts, inds, x)
+        stat = _stat_arg(seg_out) if self.use_bn else False
+        x = self.KPConv(q_pts, s_pts, inds, x, stat)
         x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True)                  # feeds unary2
-        y = self.unary2.mlp(x)                                       # raw Linear; its norm is fused below
+        y = self.unary2.mlp(x, stat)                                 # raw Linear; its norm is fused below
         shortcut = ops.max_pool(features, inds) if "strided" in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):
-            sc_raw = self.unary_shortcut.mlp(shortcut)
+            sc_raw = self.unary_shortcut.mlp(shortcut, stat)
             if self.use_bn:
                 return ops.instance_norm_act(y, seg_out, 0.1, shortcut=sc_raw, shortcut_norm=True, emit_split=True)
             return ops.add_act(y + self.unary2.batch_norm.bias, sc_raw + self.unary_shortcut.batch_norm.bias, 0.1)

@@ -55,7 +55,11 @@ int radius_query_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, fl
 
 size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K);
 int kpconv_forward_dev(const float*, int64_t, const float*, int64_t, const void*, int, int32_t, int32_t, const float*, int32_t, const float*,
-                       int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t, const void*, const void*, int32_t, const uint8_t*);
+                       int32_t, float, const float*, int32_t, float*, void*, size_t, cudaStream_t, const void*, const void*, int32_t, const uint8_t*,
+                       const int32_t*, int32_t, double*);
+int gemm_tc_core_stats_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t,
+                           const int32_t*, int, double*, int64_t);
+int colstats_final_dev(const double*, const int32_t*, int32_t, int32_t, float, float*, float*, cudaStream_t);
 int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
 void gemm_set_force_simt(int);
 void dense_set_norm_v4(int);
@@ -214,7 +218,7 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
                              pcrcg_stream_t stream)
 {
     return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
-                              cout, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr);
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr);
 }
 
 int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
@@ -224,7 +228,17 @@ int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* 
                                    pcrcg_stream_t stream)
 {
     return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
-                              cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs, row_positive);
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs, row_positive, nullptr, 0, nullptr);
+}
+
+int pcrcg_kpconv_forward_stats_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
+                                   int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi, const void* x_lo,
+                                   int32_t ldxs, const uint8_t* row_positive, int32_t cin, const float* kernel_points, int32_t K,
+                                   float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
+                                   const int32_t* seg_starts, int32_t nseg, double* stats_acc, pcrcg_stream_t stream)
+{
+    return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
+                              cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs, row_positive, seg_starts, nseg, stats_acc);
 }
 
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc, int32_t M, int32_t N,
@@ -254,6 +268,20 @@ int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, 
 {
     ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
     return gemm_tc_core_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
+}
+
+int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C, int32_t ldc,
+                                int32_t M, int32_t N, int32_t K, const float* row_scale, const int32_t* seg_starts, int32_t nseg,
+                                double* stats_acc, pcrcg_stream_t stream)
+{
+    ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
+    return gemm_tc_core_stats_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream, seg_starts, nseg, stats_acc, 0);
+}
+
+int pcrcg_colstats_final_dev(const double* stats_acc, const int32_t* seg_starts, int32_t nseg, int32_t C, float eps, float* mean, float* rstd,
+                             pcrcg_stream_t stream)
+{
+    return colstats_final_dev(stats_acc, seg_starts, nseg, C, eps, mean, rstd, (cudaStream_t)stream);
 }
 
 int pcrcg_colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,

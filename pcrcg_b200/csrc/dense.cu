@@ -298,6 +298,17 @@ int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
     return PCRCG_OK;
 }
 
+// acc [nseg][2][C] fp64 (sum, sum of squares) as accumulated by the contraction epilogue (gemm_tc.cu) -> mean / rstd
+int colstats_final_dev(const double* acc, const int32_t* seg_starts, int32_t nseg, int32_t C, float eps, float* mean, float* rstd,
+                       cudaStream_t st)
+{
+    PCRCG_REQUIRE(C >= 1 && nseg >= 1 && nseg < 65536, "instance norm: bad dimensions");
+    ProfScope prof(PC_NORM, st, 1);
+    k_colstats_final<<<(unsigned)cdiv64((int64_t)nseg * C, 256), 256, 0, st>>>(acc, seg_starts, nseg, C, eps, mean, rstd);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
 int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
                  const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
                  int32_t split_ld, uint8_t* rowflag, cudaStream_t st)

@@ -104,7 +104,17 @@ template <int BN> struct TcCfg {
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int ACC_COLS = 2 * BN;                          // D1 | D2 of one accumulator set
     static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two sets: 64, 128, 256 or 512 columns
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAT_BYTES = 4 * 32 * 17 * 4;              // per epilogue warp: 32 rows x 16 columns (pitch 17) staging
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAT_BYTES;
+};
+
+// Column statistics sink of the epilogue: per (segment, column) sum and sum of squares of the values written,
+// added in fp64 to acc[nseg][2][N] (InstanceNorm statistics without a second pass over C; dense.cu finalises them).
+struct StatSink {
+    const int32_t* seg_starts;     // [nseg + 1] absolute row starts
+    int nseg;
+    double* acc;                   // nullptr = no statistics
+    int row0;                      // absolute row of C's row 0 (chunked callers)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -116,7 +126,8 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                                              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                                                              float* __restrict__ C, int ldc, int M, int N, int K,
-                                                             const float* __restrict__ row_scale, int n_tiles_n, int total_tiles)
+                                                             const float* __restrict__ row_scale, int n_tiles_n, int total_tiles,
+                                                             const StatSink sink)
 {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -203,11 +214,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
         const int q = warp & 3;
+        float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + q * (32 * 17);
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++) {
             const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
             const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
             const int row = m0 + q * 32 + lane;
+            // statistics: the warp's 32 rows normally lie in one segment (fragment pair); a warp that straddles a boundary
+            // falls back to per-row atomics
+            int seg = 0;
+            bool seg_uniform = true;
+            if (sink.acc != nullptr) {
+                const int last = min(m0 + q * 32 + 31, M - 1);
+                if (m0 + q * 32 < M && sink.nseg > 1) {
+                    seg = cloud_of(sink.seg_starts, sink.nseg, sink.row0 + min(row, last));
+                    seg_uniform = __all_sync(0xffffffffu, seg == __shfl_sync(0xffffffffu, seg, 0));
+                }
+            }
             mbar_wait(tmem_full_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float sc = (row_scale != nullptr && row < M) ? row_scale[row] : 1.0f;
@@ -219,22 +242,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
                 tmem_ld16(trow + (uint32_t)c, d1);
                 tmem_ld16(trow + (uint32_t)(BN + c), d2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) v[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
                 if (row < M) {
                     float* o = C + (size_t)row * ldc + n0 + c;
                     if (n0 + c + 16 <= N && (ldc & 3) == 0) {
 #pragma unroll
-                        for (int u = 0; u < 16; u += 4) {
-                            float4 v;
-                            v.x = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
-                            v.y = (__uint_as_float(d1[u + 1]) + __uint_as_float(d2[u + 1])) * sc;
-                            v.z = (__uint_as_float(d1[u + 2]) + __uint_as_float(d2[u + 2])) * sc;
-                            v.w = (__uint_as_float(d1[u + 3]) + __uint_as_float(d2[u + 3])) * sc;
-                            *reinterpret_cast<float4*>(o + u) = v;
-                        }
+                        for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
                     } else {
 #pragma unroll
                         for (int u = 0; u < 16; u++)
-                            if (n0 + c + u < N) o[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
+                            if (n0 + c + u < N) o[u] = v[u];
+                    }
+                }
+                if (sink.acc != nullptr && m0 + q * 32 < M) {
+                    if (seg_uniform) {
+                        // transpose through shared memory: lane -> (column lane&15, 16-row half lane>>4)
+#pragma unroll
+                        for (int u = 0; u < 16; u++) stage[lane * 17 + u] = row < M ? v[u] : 0.f;
+                        __syncwarp();
+                        const int col = lane & 15, rb = (lane >> 4) * 16;
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float x = stage[(rb + i) * 17 + col];
+                            s1 += x;
+                            s2 = fmaf(x, x, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        if (n0 + c + col < N) {              // lanes 0-15 add the sums, lanes 16-31 the sums of squares
+                            const int which = lane >> 4;
+                            atomicAdd(sink.acc + ((size_t)seg * 2 + which) * N + n0 + c + col, (double)(which ? s2 : s1));
+                        }
+                        __syncwarp();
+                    } else if (row < M) {
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            if (n0 + c + u < N) {
+                                atomicAdd(sink.acc + ((size_t)seg * 2 + 0) * N + n0 + c + u, (double)v[u]);
+                                atomicAdd(sink.acc + ((size_t)seg * 2 + 1) * N + n0 + c + u, (double)v[u] * (double)v[u]);
+                            }
+                        }
                     }
                 }
             }
@@ -328,7 +378,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld,
 
 template <int BN>
 static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int ldk,
-                     float* C, int ldc, int M, int N, int K, const float* row_scale, cudaStream_t st)
+                     float* C, int ldc, int M, int N, int K, const float* row_scale, cudaStream_t st, const StatSink& sink)
 {
     using Cfg = TcCfg<BN>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -342,7 +392,7 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
     const long long total = cdiv64(M, TC_BM) * n_tiles_n;
     PCRCG_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
     const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);      // persistent: one CTA per SM
-    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale, n_tiles_n, (int)total);
+    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale, n_tiles_n, (int)total, sink);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }
@@ -392,18 +442,26 @@ int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int 
 }
 
 // Both operands already split: a_* bf16 [M, ldk], b_* bf16 [N, ldk] (ldk % 8 == 0).
-int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
-                     const float* row_scale, cudaStream_t st)
+int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N,
+                           int K, const float* row_scale, cudaStream_t st, const int32_t* seg_starts, int nseg, double* stats_acc, int64_t row0)
 {
+    StatSink sink{ seg_starts, nseg, stats_acc, (int)row0 };
+    PCRCG_REQUIRE(stats_acc == nullptr || (seg_starts != nullptr && nseg >= 1), "gemm_tc: statistics need segment starts");
     PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
     PCRCG_TRY(get_encode());
     count_launches(1);
     const __nv_bfloat16 *ah = (const __nv_bfloat16*)a_hi, *al = (const __nv_bfloat16*)a_lo, *bh = (const __nv_bfloat16*)b_hi,
                         *bl = (const __nv_bfloat16*)b_lo;
-    if (N % 128 == 0) return launch_tc<128>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
-    if (N % 64 == 0) return launch_tc<64>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
-    if (N % 32 == 0) return launch_tc<32>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
-    return launch_tc<16>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st);
+    if (N % 128 == 0) return launch_tc<128>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st, sink);
+    if (N % 64 == 0) return launch_tc<64>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st, sink);
+    if (N % 32 == 0) return launch_tc<32>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st, sink);
+    return launch_tc<16>(ah, al, bh, bl, ldk, C, ldc, M, N, K, row_scale, st, sink);
+}
+
+int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
+                     const float* row_scale, cudaStream_t st)
+{
+    return gemm_tc_core_stats_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, st, nullptr, 0, nullptr, 0);
 }
 
 // A already split: a_hi / a_lo bf16 [M, ldk] (ldk % 8 == 0).  B fp32, split here (weights are small).

@@ -601,14 +601,29 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
         int ja = ns;
         if (h0 + lane < H) { long long v = (long long)row[h0 + lane]; ja = (v >= 0 && v < ns) ? (int)v : ns; }
         const bool va = ja < ns;
+        // Neighbour lists are padded with shadows: a 16-neighbour k-step made of shadows only contributes exactly 0
+        // (zero-filled rows x zero weights) and is neither staged nor multiplied.  vmask is warp-uniform.
+        const uint32_t vmask = __ballot_sync(0xffffffffu, va);
+        if (vmask == 0u) continue;
+        const bool second = (vmask >> 16) != 0u;
         // feature planes: 16 unrolled cp.async of 16 bytes per lane (2 neighbour rows per step)
 #pragma unroll
-        for (int r = 0; r < AB_ROWS; r += 2) {
+        for (int r = 0; r < 16; r += 2) {
             const int j = __shfl_sync(0xffffffffu, ja, r + rsel);
             const bool v = j < ns;
             const void* src = xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs);
             const int sz = v ? 16 : 0;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(r * AB_PITCH)), "l"(src), "r"(sz) : "memory");
+        }
+        if (second) {
+#pragma unroll
+            for (int r = 16; r < AB_ROWS; r += 2) {
+                const int j = __shfl_sync(0xffffffffu, ja, r + rsel);
+                const bool v = j < ns;
+                const void* src = xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs);
+                const int sz = v ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(r * AB_PITCH)), "l"(src), "r"(sz) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         // coordinates relative to the query, squared norm (or -1 = shadow) -- one neighbour per lane
@@ -627,7 +642,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
 
 #pragma unroll
         for (int s = 0; s < AB_ROWS / 16; s++) {
-            if (h0 + 16 * s >= H) break;                    // warp-uniform
+            if (((vmask >> (16 * s)) & 0xffffu) == 0u) continue;          // warp-uniform: nothing but shadows in this k-step
             // A fragment: kernel points (g, g+8) x neighbours (2t, 2t+1 | 2t+8, 2t+9) of this 16-neighbour step
             float wv[2][4];
 #pragma unroll
@@ -750,6 +765,8 @@ int gemm_force_simt_get();
 int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi, void* b_lo, cudaStream_t st);
 int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
                      const float* row_scale, cudaStream_t st);
+int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N,
+                           int K, const float* row_scale, cudaStream_t st, const int32_t* seg_starts, int nseg, double* stats_acc, int64_t row0);
 
 // The [Nq, K*cin] aggregate is produced and consumed in chunks of query points through two
 // alternating buffers of at most WF_CHUNK_BYTES each, which bounds the workspace for very large
@@ -777,7 +794,8 @@ size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* idx, int idx_is_i64, int32_t H,
                        int32_t idx_stride, const float* x, int32_t cin, const float* kpts, int32_t K, float kp_extent,
                        const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                       const void* x_hi, const void* x_lo, int32_t ldxs, const uint8_t* rowflag_in)
+                       const void* x_hi, const void* x_lo, int32_t ldxs, const uint8_t* rowflag_in, const int32_t* seg_starts, int32_t nseg,
+                       double* stats_acc)
 {
     PCRCG_REQUIRE(K >= 1 && K <= KP_MAX - 1, "kpconv: kernel_size must be in [1,15]");
     PCRCG_REQUIRE(cin >= 1 && cout >= 1 && cout <= 2048 && H >= 0 && idx_stride >= H, "kpconv: bad dimensions");
@@ -787,6 +805,7 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     if (nq == 0) return PCRCG_OK;
     const int KC = K * cin;
     const bool tc = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC);
+    PCRCG_REQUIRE(stats_acc == nullptr || tc, "kpconv: output statistics are produced by the tensor-core contraction only");
     const int ldk = (KC + 7) / 8 * 8;
     const int64_t chunk = kpconv_chunk_rows(nq, (size_t)ldk);
     Workspace W(ws, ws_bytes);
@@ -843,7 +862,8 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
         }
         if (tc) {
             ProfScope prof(PC_GEMM, st, 0);
-            PCRCG_TRY(gemm_tc_core_dev(wf_hi, wf_lo, b_hi, b_lo, ldk, out + (size_t)r0 * cout, cout, rows, cout, KC, inv_cnt + r0, st));
+            PCRCG_TRY(gemm_tc_core_stats_dev(wf_hi, wf_lo, b_hi, b_lo, ldk, out + (size_t)r0 * cout, cout, rows, cout, KC, inv_cnt + r0, st,
+                                             seg_starts, nseg, stats_acc, r0));
         } else {
             PCRCG_TRY(gemm_dev(wf, ldk, weights, cout, 0, out + (size_t)r0 * cout, cout, rows, cout, KC, inv_cnt + r0, st));
         }

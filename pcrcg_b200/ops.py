@@ -103,8 +103,36 @@ def _idx(t):
     return t, int(t.dtype == torch.int64), t.shape[1], t.stride(0)
 
 
-def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_extent):
-    """models/blocks.py:229-374 (rigid, linear, sum).  -> [Nq, Cout] float32."""
+_fuse_stats = True
+
+
+def fuse_statistics(on):
+    """True (default): the tensor-core contractions accumulate the InstanceNorm statistics of their output in
+    the epilogue; False: separate statistics pass (pcrcg_colstats_dev) -- A/B switch for measurements."""
+    global _fuse_stats
+    _fuse_stats = bool(on)
+
+
+def _stats_begin(n, cout, stat_segments, device):
+    """-> (seg_starts, acc) for an epilogue statistics sink, or (None, None)"""
+    if stat_segments is False or not _fuse_stats or _force_simt or cout % 16 != 0 or n < 1:
+        return None, None
+    seg = _seg_starts(n, None if stat_segments is True else stat_segments, device)
+    return seg, torch.zeros((seg.shape[0] - 1, 2, cout), dtype=torch.float64, device=device)
+
+
+def _stats_end(out, seg, acc, eps=1e-5):
+    nseg, _, c = acc.shape
+    mean = torch.empty((nseg, c), dtype=torch.float32, device=out.device)
+    rstd = torch.empty((nseg, c), dtype=torch.float32, device=out.device)
+    check(lib().pcrcg_colstats_final_dev(acc.data_ptr(), seg.data_ptr(), nseg, c, float(eps), mean.data_ptr(), rstd.data_ptr(), _stream()))
+    out._pcrcg_stats = (mean, rstd, seg, float(eps))
+
+
+def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_extent, stat_segments=False):
+    """models/blocks.py:229-374 (rigid, linear, sum).  -> [Nq, Cout] float32.
+    stat_segments: False = plain; True / int32 row starts = also accumulate the InstanceNorm statistics of the
+    result in the contraction epilogue (attached as ``out._pcrcg_stats`` for :func:`instance_norm_act`)."""
     _need_cuda(q_pts, s_pts, neighb_inds, x, kernel_points, weights)
     q_pts, s_pts, x = _f32c(q_pts), _f32c(s_pts), _f32c(x)
     kernel_points, weights = _f32c(kernel_points), _f32c(weights)
@@ -119,7 +147,18 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         ws = _ws(L.pcrcg_kpconv_ws_bytes(nq, ns, cin, K), dev)
         sp = getattr(x, "_pcrcg_split", None)
-        if sp is not None and not _force_simt:
+        seg, acc = _stats_begin(nq, cout, stat_segments, dev)
+        if acc is not None and K * cin >= 16:
+            hi, lo, ld = sp if sp is not None else (None, None, 0)
+            rp = getattr(x, "_pcrcg_rowpos", None) if sp is not None else None
+            check(L.pcrcg_kpconv_forward_stats_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
+                                                   x.data_ptr(), hi.data_ptr() if hi is not None else None,
+                                                   lo.data_ptr() if lo is not None else None, ld,
+                                                   rp.data_ptr() if rp is not None else None, cin, kernel_points.data_ptr(), K,
+                                                   float(KP_extent), weights.data_ptr(), cout, out.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), seg.data_ptr(), seg.shape[0] - 1, acc.data_ptr(), _stream()))
+            _stats_end(out, seg, acc)
+        elif sp is not None and not _force_simt:
             hi, lo, ld = sp
             rp = getattr(x, "_pcrcg_rowpos", None)
             check(L.pcrcg_kpconv_forward_split_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
@@ -142,10 +181,10 @@ def _split_planes(n, c, device):
     return (torch.empty((n, ld), dtype=torch.bfloat16, device=device), torch.empty((n, ld), dtype=torch.bfloat16, device=device), ld)
 
 
-def linear(x, weight):
+def linear(x, weight, stat_segments=False):
     """nn.Linear(bias=False): x [N,Cin] @ weight[Cout,Cin]^T   (models/blocks.py:490,497).
     If the producer of ``x`` attached its bf16 (hi, lo) planes (``x._pcrcg_split``) the tensor-core
-    contraction consumes them directly."""
+    contraction consumes them directly.  stat_segments: see :func:`kpconv_forward`."""
     _need_cuda(x, weight)
     x, weight = _f32c(x), _f32c(weight)
     n, cin = x.shape
@@ -158,8 +197,14 @@ def linear(x, weight):
             hi, lo, ld = sp
             bh, bl, _ = _split_planes(cout, cin, x.device)
             check(L.pcrcg_split_bf16_dev(weight.data_ptr(), cin, cout, cin, bh.data_ptr(), bl.data_ptr(), ld, _stream()))
-            check(L.pcrcg_gemm_bf16x3_dev(hi.data_ptr(), lo.data_ptr(), bh.data_ptr(), bl.data_ptr(), ld, out.data_ptr(), cout, n, cout, cin,
-                                          None, _stream()))
+            seg, acc = _stats_begin(n, cout, stat_segments, x.device)
+            if acc is not None:
+                check(L.pcrcg_gemm_bf16x3_stats_dev(hi.data_ptr(), lo.data_ptr(), bh.data_ptr(), bl.data_ptr(), ld, out.data_ptr(), cout, n, cout,
+                                                    cin, None, seg.data_ptr(), seg.shape[0] - 1, acc.data_ptr(), _stream()))
+                _stats_end(out, seg, acc)
+            else:
+                check(L.pcrcg_gemm_bf16x3_dev(hi.data_ptr(), lo.data_ptr(), bh.data_ptr(), bl.data_ptr(), ld, out.data_ptr(), cout, n, cout, cin,
+                                              None, _stream()))
         else:
             check(L.pcrcg_gemm_dev(x.data_ptr(), cin, weight.data_ptr(), cin, 1, out.data_ptr(), cout, n, cout, cin, None, _stream()))
     return out
@@ -195,20 +240,30 @@ def column_stats(x, segments=None, eps=1e-5):
     return mean, rstd, seg
 
 
+def _stats_of(x, segments, eps):
+    """statistics attached by the producing contraction (same eps, same segment tensor) or a pass over x"""
+    st = getattr(x, "_pcrcg_stats", None)
+    if st is not None and st[3] == float(eps) and x.dtype == torch.float32 and x.is_contiguous():
+        mean, rstd, seg, _ = st
+        if (segments is None and seg.shape[0] == 2) or (segments is not None and seg.data_ptr() == _i32c(segments).data_ptr()):
+            return mean, rstd, seg
+    return column_stats(x, segments, eps)
+
+
 def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5, emit_split=False,
                       emit_rowpos=False):
     """act(IN(x) + [IN](shortcut)) with act = LeakyReLU(slope) or identity (slope=None).
     models/blocks.py:456-463 (+ :501, :590, :662, :678).  emit_split: also write the bf16 (hi, lo)
     planes of the result (attached as ``out._pcrcg_split``) for a following :func:`linear`."""
     _need_cuda(x, shortcut)
-    x = _f32c(x)
     n, c = x.shape
-    mean, rstd, seg = column_stats(x, segments, eps)
+    mean, rstd, seg = _stats_of(x, segments, eps)
+    x = _f32c(x)
     scm = scr = None
     if shortcut is not None:
-        shortcut = _f32c(shortcut)
         if shortcut_norm:
-            scm, scr, _ = column_stats(shortcut, segments, eps)
+            scm, scr, _ = _stats_of(shortcut, segments, eps)
+        shortcut = _f32c(shortcut)
     out = torch.empty_like(x)
     p = lambda t: t.data_ptr() if t is not None else None
     sp = _split_planes(n, c, x.device) if (emit_split and c % 8 == 0 and not _force_simt) else None

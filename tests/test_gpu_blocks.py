@@ -198,3 +198,36 @@ def test_calibrate_neighbors_equals_reference_rule():
     cs = np.cumsum(hists.T, axis=0)
     want = np.sum(cs < 0.8 * cs[hist_n - 1, :], axis=0)
     assert got.tolist() == want.tolist()
+
+
+def test_kpconv_shadow_steps_anywhere_and_epilogue_statistics():
+    """(1) the bf16 aggregation skips 16-neighbour steps made of shadows only: lists whose shadows sit at the FRONT or
+    in the middle (legal for the KPConv API, never produced by the search) must give the same result; (2) the
+    statistics accumulated by the contraction epilogue equal those of the written output."""
+    src, tgt, _ = synthetic.match3d_pair(9, n_target=1100)
+    pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+    rows = ops.batch_query(_d(pts), _d(pts), _d(lens), _d(lens), 0.0625, 39).cpu()
+    n = len(pts)
+    shadow = torch.full((n, 16), n, dtype=rows.dtype)
+    variants = {"front": torch.cat([shadow, rows], 1), "middle": torch.cat([rows[:, :8], shadow, shadow, rows[:, 8:]], 1),
+                "all": torch.full((n, 40), n, dtype=rows.dtype)}
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn(n, 64, generator=g).to(DEV)
+    x = ops.instance_norm_act(raw, None, 0.1, emit_split=True, emit_rowpos=True)
+    w = torch.randn(15, 64, 64, generator=g) / 31.0
+    kp = torch.randn(15, 3, generator=g) * 0.03
+    seg = torch.tensor([0, int(lens[0]) // 2, n], dtype=torch.int32, device=DEV)
+    for name, idx in variants.items():
+        ref = bp.kpconv(torch.from_numpy(pts), torch.from_numpy(pts), idx, x.cpu(), kp, w, 0.05)
+        out = ops.kpconv_forward(_d(pts), _d(pts), idx.to(DEV), x, kp.to(DEV), w.to(DEV), 0.05, stat_segments=seg)
+        if name == "all":
+            assert float(out.abs().max()) == 0.0 and float(ref.abs().max()) == 0.0
+            continue
+        assert _err(out, ref) < 1e-4, name
+        mean, rstd, _, _ = out._pcrcg_stats
+        for k in range(2):
+            blk_ = out[int(seg[k]):int(seg[k + 1])].double()
+            mu = blk_.mean(0)
+            var = (blk_ * blk_).mean(0) - mu * mu
+            assert float((mean[k].double() - mu).abs().max()) < 1e-6 + 1e-5 * float(mu.abs().max())
+            assert float(((rstd[k].double() - 1 / torch.sqrt(var + 1e-5)).abs() * torch.sqrt(var + 1e-5)).max()) < 1e-4

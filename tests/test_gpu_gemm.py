@@ -58,3 +58,44 @@ def test_large_and_repeatable():
     assert _err(o1[:4096], ref) < 5e-5
     ref = a[-4096:].double() @ b.double()
     assert _err(o1[-4096:], ref) < 5e-5
+
+
+def _ref_stats(out, seg, eps=1e-5):
+    means, rstds = [], []
+    for a, b in zip(seg[:-1], seg[1:]):
+        blk = out[a:b].double()
+        mu = blk.mean(0)
+        var = (blk * blk).mean(0) - mu * mu
+        means.append(mu)
+        rstds.append(1.0 / torch.sqrt(var.clamp_min(0) + eps))
+    return torch.stack(means), torch.stack(rstds)
+
+
+@pytest.mark.parametrize("M,N,K,seg", [
+    (1000, 256, 64, None),                       # one group (the reference's case)
+    (4097, 64, 256, [0, 1000, 1031, 4097]),      # boundaries inside a 32-row epilogue warp and inside a tile
+    (777, 16, 48, [0, 128, 777]),                # boundary on a tile edge, narrow N
+    (5000, 2048, 128, [0, 2500, 5000]),
+    (130, 512, 512, [0, 1, 130]),                # a one-row segment
+])
+def test_linear_epilogue_statistics(M, N, K, seg):
+    """InstanceNorm statistics accumulated by the contraction epilogue == statistics of the written output
+    (fp64 torch), and instance_norm_act consumes them (same result as the separate statistics pass)."""
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) + 0.3).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    hi, lo, ld = ops._split_planes(M, K, x.device)
+    from pcrcg_b200._lib import lib, check
+    check(lib().pcrcg_split_bf16_dev(x.data_ptr(), K, M, K, hi.data_ptr(), lo.data_ptr(), ld, torch.cuda.current_stream().cuda_stream))
+    x._pcrcg_split = (hi, lo, ld)
+    segt = None if seg is None else torch.tensor(seg, dtype=torch.int32, device=DEV)
+    out = ops.linear(x, w, stat_segments=True if segt is None else segt)
+    assert hasattr(out, "_pcrcg_stats"), "tensor-core path must attach the statistics"
+    mean, rstd, _, _ = out._pcrcg_stats
+    rm, rr = _ref_stats(out, seg or [0, M])
+    assert float((mean.double() - rm).abs().max()) < 1e-5 * float(rm.abs().max().clamp_min(1.0))
+    assert float(((rstd.double() - rr).abs() / rr).max()) < 1e-4
+    fused = ops.instance_norm_act(out, segt, 0.1)
+    plain = out.clone()                          # no attribute -> separate statistics pass
+    sep = ops.instance_norm_act(plain, segt, 0.1)
+    assert float((fused - sep).abs().max()) < 2e-4 * float(sep.abs().max())
