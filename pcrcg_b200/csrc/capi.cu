@@ -62,6 +62,7 @@ int gemm_tc_core_stats_dev(const void*, const void*, const void*, const void*, i
 int colstats_final_dev(const double*, const int32_t*, int32_t, int32_t, float, float*, float*, cudaStream_t);
 int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, int, const float*, cudaStream_t);
 void gemm_set_force_simt(int);
+void gemm_set_stats_dbg(int);
 void dense_set_norm_v4(int);
 void kpconv_set_agg_simt(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
@@ -253,6 +254,7 @@ int pcrcg_set_option(const char* name, int32_t value)
 {
     if (!strcmp(name, "contraction_simt")) gemm_set_force_simt(value);
     else if (!strcmp(name, "aggregate_simt")) kpconv_set_agg_simt(value);
+    else if (!strcmp(name, "stats_debug")) gemm_set_stats_dbg(value);
     else if (!strcmp(name, "norm_vectorised")) dense_set_norm_v4(value);
     else { set_error("pcrcg_set_option: unknown option '%s'", name); return PCRCG_ERR; }
     return PCRCG_OK;

@@ -8,7 +8,7 @@
 // feature tolerance with margin where a single bf16 (2e-3) or tf32 (3e-4 per op, 11 stacked blocks)
 // pass is not.
 //
-// Kernel (PERSISTENT: one CTA per SM loops over 128 x BN output tiles, 192 threads; the accumulator is
+// Kernel (PERSISTENT: one CTA per SM loops over 128 x BN output tiles, 192 or 320 threads; the accumulator is
 // double buffered in TMEM so the epilogue of tile i overlaps the TMA loads and MMAs of tile i+1):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor 2D loads of the four operand tiles of a
 //              64-wide K block (A_hi, A_lo [128 x 64], B_hi, B_lo [BN x 64], 128B swizzle) into a
@@ -17,7 +17,9 @@
 //                 D[:, 0:2BN] += A_hi * [B_hi ; B_lo]^T      (one instruction, N = 2*BN)
 //                 D[:, 0:BN]  += A_lo * B_hi^T
 //              accumulators live in TMEM (2*BN fp32 columns); tcgen05.commit frees the smem slot
-//   warps 2-5: epilogue -- tcgen05.ld 32x32b, (D1 + D2) * row_scale, vector stores to global
+//   warps 2-5 (2-9 for BN >= 64): epilogue -- tcgen05.ld 32x32b, (D1 + D2) * row_scale, shared-memory transpose, row-segment
+//              stores to global; optionally the per-(segment, column) sum / sum of squares of the tile for the InstanceNorm
+//              that follows every contraction of the path (saves a full read pass over C)
 #include "common.cuh"
 
 #include <cuda.h>
@@ -27,7 +29,6 @@ namespace pcrcg {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per K block = one 128-byte swizzle atom
-constexpr int TC_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -104,8 +105,11 @@ template <int BN> struct TcCfg {
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int ACC_COLS = 2 * BN;                          // D1 | D2 of one accumulator set
     static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two sets: 64, 128, 256 or 512 columns
-    static constexpr int STAT_BYTES = 4 * 32 * 17 * 4;              // per epilogue warp: 32 rows x 16 columns (pitch 17) staging
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAT_BYTES;
+    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;               // two warps per TMEM lane quarter for wide tiles
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int STAT_BYTES = EPI_WARPS * 32 * 20 * 4;       // per epilogue warp: 32 rows x 16 columns (pitch 20 floats) staging
+    static constexpr int SEG_CACHE = 256;                            // segment starts cached in shared memory (else read from global)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAT_BYTES + (SEG_CACHE + 4) * 4;
 };
 
 // Column statistics sink of the epilogue: per (segment, column) sum and sum of squares of the values written,
@@ -115,7 +119,10 @@ struct StatSink {
     int nseg;
     double* acc;                   // nullptr = no statistics
     int row0;                      // absolute row of C's row 0 (chunked callers)
+    int dbg;                       // measurement switch: 1 = no atomics, 2 = no column sums
 };
+static int g_stats_dbg = 0;
+void gemm_set_stats_dbg(int v) { g_stats_dbg = v; }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
@@ -123,7 +130,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 }
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) k_gemm_bf16x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                                              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                                                              float* __restrict__ C, int ldc, int M, int N, int K,
                                                              const float* __restrict__ row_scale, int n_tiles_n, int total_tiles,
@@ -151,13 +158,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), Cfg::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // segment starts of the statistics sink: a shared-memory copy keeps the per-tile segment lookup of the epilogue off the
+    // (heavily loaded) global-memory path
+    int32_t* seg_cache = reinterpret_cast<int32_t*>(smem_raw + (bar_base + 256u + (uint32_t)Cfg::STAT_BYTES - smem_u32(smem_raw)));
+    const bool seg_cached = sink.acc != nullptr && sink.nseg <= Cfg::SEG_CACHE;
+    if (seg_cached)
+        for (int i = threadIdx.x; i <= sink.nseg; i += blockDim.x) seg_cache[i] = sink.seg_starts[i];
+    const int32_t* segp = seg_cached ? seg_cache : sink.seg_starts;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -212,86 +226,136 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bf16x3(const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
-        const int q = warp & 3;
-        float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + q * (32 * 17);
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32); with 8 epilogue warps (BN >= 64) the two warps of a
+        // lane quarter split the tile's columns =====
+        // Per chunk of 16 columns: tcgen05.ld (the next chunk's loads are in flight while this one is processed) -> (D1 + D2)
+        // * row_scale -> the warp's 32 x 16 block is staged in shared memory so that (a) global stores are whole row segments
+        // (8 rows x 64 B per instruction instead of 32 scattered 16-byte pieces) and (b) columns can be summed for the
+        // InstanceNorm statistics.  Statistics stay in per-lane fp64 registers while the CTA remains inside one segment
+        // (its n-tile never changes: the grid is a multiple of n_tiles_n) and are flushed with one atomic per column.
+        constexpr int EW = Cfg::EPI_WARPS;
+        constexpr int WCOLS = EW == 8 ? BN / 2 : BN;               // columns of the tile handled by one warp
+        constexpr int CH = 16, NCH = WCOLS / CH;
+        constexpr int PITCH = 20;                                  // floats: 16-byte aligned rows; conflict-free STS.128 / LDS.128
+        const int ew = warp - 2, q = warp & 3;
+        const int wc0 = EW == 8 ? (ew >> 2) * WCOLS : 0;           // first column (inside the tile) of this warp
+        float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + ew * (32 * PITCH);
+        const bool stats = sink.acc != nullptr;
+        double a1[NCH], a2[NCH];                                   // lanes 0-15: column sums, lanes 16-31: sums of squares
+#pragma unroll
+        for (int i = 0; i < NCH; i++) a1[i] = 0.0;
+        (void)a2;
+        int acc_seg = -1, acc_n0 = 0, cur_seg = 0;
+        auto flush = [&]() {
+            if (acc_seg >= 0 && !(sink.dbg & 1)) {
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    const int col = acc_n0 + wc0 + i * CH + (lane & 15);
+                    if (col < N) atomicAdd(sink.acc + ((size_t)acc_seg * 2 + (lane >> 4)) * N + col, a1[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NCH; i++) a1[i] = 0.0;
+        };
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, t++) {
             const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
             const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
-            const int row = m0 + q * 32 + lane;
-            // statistics: the warp's 32 rows normally lie in one segment (fragment pair); a warp that straddles a boundary
-            // falls back to per-row atomics
+            const int wrow0 = m0 + q * 32, row = wrow0 + lane;
+            const bool wvalid = wrow0 < M;
             int seg = 0;
             bool seg_uniform = true;
-            if (sink.acc != nullptr) {
-                const int last = min(m0 + q * 32 + 31, M - 1);
-                if (m0 + q * 32 < M && sink.nseg > 1) {
-                    seg = cloud_of(sink.seg_starts, sink.nseg, sink.row0 + min(row, last));
-                    seg_uniform = __all_sync(0xffffffffu, seg == __shfl_sync(0xffffffffu, seg, 0));
+            if (stats && wvalid) {
+                if (sink.nseg > 1) {
+                    // m0 only grows: advance the segment cursor (warp-uniform, normally zero or one step)
+                    const int first = sink.row0 + wrow0, last = sink.row0 + min(wrow0 + 31, M - 1);
+                    while (cur_seg + 1 < sink.nseg && first >= segp[cur_seg + 1]) cur_seg++;
+                    seg = cur_seg;
+                    seg_uniform = cur_seg + 1 >= sink.nseg || last < segp[cur_seg + 1];
+                    if (!seg_uniform) {               // rare: per-row lookup (generic loads: segp may point to shared memory)
+                        const int r = sink.row0 + min(row, M - 1);
+                        seg = cur_seg;
+                        while (seg + 1 < sink.nseg && r >= segp[seg + 1]) seg++;
+                    }
+                }
+                if (seg_uniform && (seg != acc_seg || n0 != acc_n0)) {
+                    flush();
+                    acc_seg = seg;
+                    acc_n0 = n0;
                 }
             }
             mbar_wait(tmem_full_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float sc = (row_scale != nullptr && row < M) ? row_scale[row] : 1.0f;
-            const uint32_t trow = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                if (n0 + c >= N) break;                      // warp-uniform
-                uint32_t d1[16], d2[16];
-                tmem_ld16(trow + (uint32_t)c, d1);
-                tmem_ld16(trow + (uint32_t)(BN + c), d2);
+            const uint32_t trow = tmem_base + acc * Cfg::ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)wc0;
+            uint32_t d[2][2 * CH];
+            tmem_ld16(trow, d[0]);
+            tmem_ld16(trow + (uint32_t)BN, d[0] + CH);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float v[16];
+                float v[CH];
 #pragma unroll
-                for (int u = 0; u < 16; u++) v[u] = (__uint_as_float(d1[u]) + __uint_as_float(d2[u])) * sc;
-                if (row < M) {
-                    float* o = C + (size_t)row * ldc + n0 + c;
-                    if (n0 + c + 16 <= N && (ldc & 3) == 0) {
-#pragma unroll
-                        for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 16; u++)
-                            if (n0 + c + u < N) o[u] = v[u];
-                    }
+                for (int u = 0; u < CH; u++) v[u] = (__uint_as_float(d[ch & 1][u]) + __uint_as_float(d[ch & 1][CH + u])) * sc;
+                if (ch + 1 < NCH) {
+                    tmem_ld16(trow + (uint32_t)((ch + 1) * CH), d[(ch + 1) & 1]);
+                    tmem_ld16(trow + (uint32_t)(BN + (ch + 1) * CH), d[(ch + 1) & 1] + CH);
                 }
-                if (sink.acc != nullptr && m0 + q * 32 < M) {
+#pragma unroll
+                for (int u = 0; u < CH; u += 4)
+                    *reinterpret_cast<float4*>(stage + lane * PITCH + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+                __syncwarp();
+                const int cbase = n0 + wc0 + ch * CH;
+                if ((ldc & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {                       // 8 rows x 64 bytes per instruction
+                        const int r = j * 8 + (lane >> 2), piece = (lane & 3) * 4;
+                        if (wrow0 + r < M && cbase + piece < N)
+                            *reinterpret_cast<float4*>(C + (size_t)(wrow0 + r) * ldc + cbase + piece) =
+                                *reinterpret_cast<const float4*>(stage + r * PITCH + piece);
+                    }
+                } else if (lane < CH && cbase + lane < N) {
+                    for (int r = 0; r < 32 && wrow0 + r < M; r++) C[(size_t)(wrow0 + r) * ldc + cbase + lane] = stage[r * PITCH + lane];
+                }
+                if (stats && wvalid && !(sink.dbg & 2)) {
+                    const int cl = lane & 15, rh = lane >> 4;
                     if (seg_uniform) {
-                        // transpose through shared memory: lane -> (column lane&15, 16-row half lane>>4)
+                        // half-warp rh sums rows (i/4)*8 + i%4 + 4*rh (bank-conflict free with pitch 20); rows >= M hold exact
+                        // zeros (TMA zero fill of A)
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
-                        for (int u = 0; u < 16; u++) stage[lane * 17 + u] = row < M ? v[u] : 0.f;
-                        __syncwarp();
-                        const int col = lane & 15, rb = (lane >> 4) * 16;
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float x = stage[(rb + i) * 17 + col];
-                            s1 += x;
-                            s2 = fmaf(x, x, s2);
+                        for (int i = 0; i < 16; i += 2) {
+                            const float x = stage[((i >> 2) * 8 + (i & 3) + 4 * rh) * PITCH + cl];
+                            const float y = stage[(((i + 1) >> 2) * 8 + ((i + 1) & 3) + 4 * rh) * PITCH + cl];
+                            s1a += x; s2a = fmaf(x, x, s2a);
+                            s1b += y; s2b = fmaf(y, y, s2b);
                         }
+                        float s1 = s1a + s1b, s2 = s2a + s2b;
                         s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
                         s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                        if (n0 + c + col < N) {              // lanes 0-15 add the sums, lanes 16-31 the sums of squares
-                            const int which = lane >> 4;
-                            atomicAdd(sink.acc + ((size_t)seg * 2 + which) * N + n0 + c + col, (double)(which ? s2 : s1));
-                        }
-                        __syncwarp();
-                    } else if (row < M) {
-#pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            if (n0 + c + u < N) {
-                                atomicAdd(sink.acc + ((size_t)seg * 2 + 0) * N + n0 + c + u, (double)v[u]);
-                                atomicAdd(sink.acc + ((size_t)seg * 2 + 1) * N + n0 + c + u, (double)v[u] * (double)v[u]);
+                        a1[ch] += (double)(rh ? s2 : s1);
+                    } else {
+                        // the warp's rows straddle a segment boundary: one masked column sum per segment, straight to memory
+                        const int sfirst = __shfl_sync(0xffffffffu, seg, 0), slast = __shfl_sync(0xffffffffu, seg, 31);
+                        for (int sg = sfirst; sg <= slast; sg++) {
+                            float s1 = 0.f, s2 = 0.f;
+                            for (int i = 0; i < 32; i++) {
+                                const int si = __shfl_sync(0xffffffffu, seg, i);
+                                const float x = stage[i * PITCH + cl];
+                                if (si == sg && wrow0 + i < M) { s1 += x; s2 = fmaf(x, x, s2); }
                             }
+                            if (cbase + cl < N && !(sink.dbg & 1))
+                                atomicAdd(sink.acc + ((size_t)sg * 2 + rh) * N + cbase + cl, (double)(rh ? s2 : s1));
                         }
                     }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
+        if (stats) flush();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -391,8 +455,10 @@ static int launch_tc(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const
     const int n_tiles_n = (int)cdiv64(N, BN);
     const long long total = cdiv64(M, TC_BM) * n_tiles_n;
     PCRCG_REQUIRE(total < (1ll << 31), "gemm_tc: too many tiles");
-    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);      // persistent: one CTA per SM
-    k_gemm_bf16x3<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale, n_tiles_n, (int)total, sink);
+    // persistent: one CTA per SM; a multiple of n_tiles_n so that a CTA keeps its n-tile (epilogue statistics stay in registers)
+    unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+    if ((int)grid > n_tiles_n) grid -= grid % (unsigned)n_tiles_n;
+    k_gemm_bf16x3<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, C, ldc, M, N, K, row_scale, n_tiles_n, (int)total, sink);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }
@@ -445,7 +511,7 @@ int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int 
 int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N,
                            int K, const float* row_scale, cudaStream_t st, const int32_t* seg_starts, int nseg, double* stats_acc, int64_t row0)
 {
-    StatSink sink{ seg_starts, nseg, stats_acc, (int)row0 };
+    StatSink sink{ seg_starts, nseg, stats_acc, (int)row0, g_stats_dbg };
     PCRCG_REQUIRE(stats_acc == nullptr || (seg_starts != nullptr && nseg >= 1), "gemm_tc: statistics need segment starts");
     PCRCG_REQUIRE(gemm_tc_shape_ok(M, N, K) && ldk % 8 == 0 && ldk >= K, "gemm_tc: unsupported shape M=%d N=%d K=%d ldk=%d", M, N, K, ldk);
     PCRCG_TRY(get_encode());

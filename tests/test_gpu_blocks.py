@@ -224,6 +224,8 @@ def test_kpconv_shadow_steps_anywhere_and_epilogue_statistics():
             assert float(out.abs().max()) == 0.0 and float(ref.abs().max()) == 0.0
             continue
         assert _err(out, ref) < 1e-4, name
+        if not hasattr(out, "_pcrcg_stats"):       # fp32 CUDA-core contraction (parity anchor): separate statistics pass
+            continue
         mean, rstd, _, _ = out._pcrcg_stats
         for k in range(2):
             blk_ = out[int(seg[k]):int(seg[k + 1])].double()

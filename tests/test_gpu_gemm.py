@@ -94,7 +94,10 @@ def test_linear_epilogue_statistics(M, N, K, seg):
     mean, rstd, _, _ = out._pcrcg_stats
     rm, rr = _ref_stats(out, seg or [0, M])
     assert float((mean.double() - rm).abs().max()) < 1e-5 * float(rm.abs().max().clamp_min(1.0))
-    assert float(((rstd.double() - rr).abs() / rr).max()) < 1e-4
+    # variance = E[x^2] - mean^2 with fp32 partial sums per 32-row block (as the separate statistics pass): absolute
+    # error ~1e-7 E[x^2]; compared as variances so that a degenerate one-row segment (var = 0, rstd = eps^-1/2) is judged fairly
+    var, var_ref = 1.0 / rstd.double() ** 2 - 1e-5, 1.0 / rr ** 2 - 1e-5
+    assert float(((var - var_ref).abs() / (var_ref + rm * rm + 1e-5)).max()) < 2e-6
     fused = ops.instance_norm_act(out, segt, 0.1)
     plain = out.clone()                          # no attribute -> separate statistics pass
     sep = ops.instance_norm_act(plain, segt, 0.1)

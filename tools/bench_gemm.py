@@ -21,7 +21,12 @@ def main():
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    for a in sys.argv:
+        if a.startswith("--dbg="):
+            check(L.pcrcg_set_option(b"stats_debug", int(a[6:])))
     for name, M, N, K in SHAPES:
+        if "--wide" in sys.argv and N < 256:
+            continue
         ldk = (K + 7) // 8 * 8
         a = torch.randn(M, K, device=dev)
         b = torch.randn(N, K, device=dev) / K ** 0.5
@@ -30,7 +35,13 @@ def main():
         c = torch.empty(M, N, device=dev)
         check(L.pcrcg_split_bf16_dev(a.data_ptr(), K, M, K, ah.data_ptr(), al.data_ptr(), ldk, st))
         check(L.pcrcg_split_bf16_dev(b.data_ptr(), K, N, K, bh.data_ptr(), bl.data_ptr(), ldk, st))
-        run = lambda: check(L.pcrcg_gemm_bf16x3_dev(ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), ldk, c.data_ptr(), N, M, N, K, None, st))
+        if "--stats" in sys.argv:        # epilogue InstanceNorm statistics, 16 segments
+            seg = torch.linspace(0, M, 17, device=dev).to(torch.int32)
+            acc = torch.zeros(16, 2, N, dtype=torch.float64, device=dev)
+            run = lambda: check(L.pcrcg_gemm_bf16x3_stats_dev(ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), ldk, c.data_ptr(), N, M, N, K,
+                                                              None, seg.data_ptr(), 16, acc.data_ptr(), st))
+        else:
+            run = lambda: check(L.pcrcg_gemm_bf16x3_dev(ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), ldk, c.data_ptr(), N, M, N, K, None, st))
         for _ in range(3):
             run()
         ts = []
