@@ -87,7 +87,8 @@ int pcrcg_kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts,
                              float* out, void* ws, size_t ws_bytes, pcrcg_stream_t stream);
 
 /* Same, with the features ALSO available as bf16 (hi, lo) planes [ns, ldxs] (x = hi + lo; emitted by
- * pcrcg_norm_act_dev): the aggregation then runs its bf16x3 ldmatrix / mma.m16n8k16 kernel. */
+ * pcrcg_norm_act_dev): the aggregation then runs its bf16x3 ldmatrix / mma.m16n8k16 kernel.  x may then be NULL if
+ * row_positive is given, cin % 64 == 0 and cout % 16 == 0 (features that exist as planes only). */
 int pcrcg_kpconv_forward_split_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* neighb_inds,
                                    int32_t idx_is_i64, int32_t H, int32_t idx_stride, const float* x, const void* x_hi,
                                    const void* x_lo, int32_t ldxs, const uint8_t* row_positive /* may be NULL */, int32_t cin,
@@ -136,6 +137,7 @@ int pcrcg_set_option(const char* name, int32_t value);
  *   act = LeakyReLU(slope) when slope >= 0, identity when slope < 0;  mean == NULL skips the normalisation.
  * split_hi / split_lo (bf16 [n, split_ld], may be NULL): the result is ALSO emitted as the (hi, lo) planes the
  * next tensor-core contraction consumes, saving that contraction's own split pass.
+ * out may be NULL when the planes are requested (a result consumed only by tensor-core contractions: saves the fp32 write).
  * row_positive (uint8 [n], may be NULL; needs a power-of-two C): flag[r] = (sum_c out[r,c] > 0), the per-row
  * predicate of the KPConv neighbour count (models/blocks.py:369-370), saving the consumer a pass over out.
  * ------------------------------------------------------------------------------------------- */

@@ -90,9 +90,9 @@ class BatchNormBlock(nn.Module):
         if not use_bn:
             self.bias = Parameter(torch.zeros(in_dim, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, x, segments=None, slope=None, emit_split=False, emit_rowpos=False):
+    def forward(self, x, segments=None, slope=None, emit_split=False, emit_rowpos=False, planes_only=False):
         if self.use_bn:
-            return ops.instance_norm_act(x, segments, slope, emit_split=emit_split, emit_rowpos=emit_rowpos)
+            return ops.instance_norm_act(x, segments, slope, emit_split=emit_split, emit_rowpos=emit_rowpos, planes_only=planes_only)
         x = x + self.bias
         return x if slope is None else torch.nn.functional.leaky_relu(x, slope)
 
@@ -117,9 +117,10 @@ class UnaryBlock(nn.Module):
         self.mlp = _Linear(in_dim, out_dim)
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
-    def forward(self, x, batch=None, segments=None, emit_split=False, emit_rowpos=False):
+    def forward(self, x, batch=None, segments=None, emit_split=False, emit_rowpos=False, planes_only=False):
         y = self.mlp(x, _stat_arg(segments) if self.use_bn else False)
-        return self.batch_norm(y, segments, None if self.no_relu else 0.1, emit_split=emit_split, emit_rowpos=emit_rowpos)
+        return self.batch_norm(y, segments, None if self.no_relu else 0.1, emit_split=emit_split, emit_rowpos=emit_rowpos,
+                               planes_only=planes_only)
 
 
 class LastUnaryBlock(nn.Module):
@@ -178,10 +179,12 @@ class ResnetBottleneckBlock(nn.Module):
         q_pts, s_pts, inds, out_layer = _block_geometry(self.block_name, self.layer_ind, batch)
         seg_in, seg_out = _segments(batch, self.layer_ind), _segments(batch, out_layer)
         # unary1's output is gathered by the KPConv aggregation: emit its bf16 planes for the bf16x3 kernel
-        x = self.unary1(features, segments=seg_in, emit_split=True, emit_rowpos=True) if isinstance(self.unary1, UnaryBlock) else features
+        # (both intermediates below never leave the block and feed tensor-core contractions only: no fp32 copy is written)
+        x = (self.unary1(features, segments=seg_in, emit_split=True, emit_rowpos=True, planes_only=True)
+             if isinstance(self.unary1, UnaryBlock) else features)
         stat = _stat_arg(seg_out) if self.use_bn else False
         x = self.KPConv(q_pts, s_pts, inds, x, stat)
-        x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True)                  # feeds unary2
+        x = self.batch_norm_conv(x, seg_out, 0.1, emit_split=True, planes_only=True)   # feeds unary2
         y = self.unary2.mlp(x, stat)                                 # raw Linear; its norm is fused below
         shortcut = ops.max_pool(features, inds) if "strided" in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):

@@ -64,6 +64,7 @@ int gemm_dev(const float*, int, const float*, int, int, float*, int, int, int, i
 void gemm_set_force_simt(int);
 void gemm_set_stats_dbg(int);
 void dense_set_norm_v4(int);
+void dense_set_norm_variant(int);
 void kpconv_set_agg_simt(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
@@ -255,6 +256,7 @@ int pcrcg_set_option(const char* name, int32_t value)
     if (!strcmp(name, "contraction_simt")) gemm_set_force_simt(value);
     else if (!strcmp(name, "aggregate_simt")) kpconv_set_agg_simt(value);
     else if (!strcmp(name, "stats_debug")) gemm_set_stats_dbg(value);
+    else if (!strcmp(name, "norm_variant")) dense_set_norm_variant(value);
     else if (!strcmp(name, "norm_vectorised")) dense_set_norm_v4(value);
     else { set_error("pcrcg_set_option: unknown option '%s'", name); return PCRCG_ERR; }
     return PCRCG_OK;

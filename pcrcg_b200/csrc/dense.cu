@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_norm_act(const float* __restrict__ x, i
             v += s;
         }
         if (slope >= 0.f) v = v > 0.f ? v : v * slope;
-        out[(size_t)r * ldo + c] = v;
+        if (out != nullptr) out[(size_t)r * ldo + c] = v;
         vv[u] = v;
     }
     if (hi != nullptr) {          // bf16 (hi, lo) planes of the result for the next tensor-core contraction (lds % 8 == 0)
@@ -113,14 +113,14 @@ __global__ void __launch_bounds__(256) k_norm_act(const float* __restrict__ x, i
 // Vectorised variant (C % 4 == 0): a thread owns one 4-channel group (mean / rstd in registers) and
 // NA_UNROLL rows whose float4 loads are all issued before the arithmetic; a block covers
 // (256 / column groups) * NA_UNROLL consecutive rows and re-reads the statistics if it crosses a segment.
-constexpr int NA_UNROLL = 4;
 
 __device__ __forceinline__ float4 na_apply(float4 v, float4 mu, float4 rs)
 {
     return make_float4((v.x - mu.x) * rs.x, (v.y - mu.y) * rs.y, (v.z - mu.z) * rs.z, (v.w - mu.w) * rs.w);
 }
 
-__global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x, int n, int C, const int32_t* __restrict__ seg_starts,
+template <int NA_UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_norm_act_v4(const float* __restrict__ x, int n, int C, const int32_t* __restrict__ seg_starts,
                                                      int nseg, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ sc, const float* __restrict__ sc_mean,
                                                      const float* __restrict__ sc_rstd, float slope, float* __restrict__ out,
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_norm_act_v4(const float* __restrict__ x
                 o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
                 o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
             }
-            *reinterpret_cast<float4*>(out + (size_t)r * C + 4 * cg) = o;
+            if (out != nullptr) *reinterpret_cast<float4*>(out + (size_t)r * C + 4 * cg) = o;
             rsum[u] += (o.x + o.y) + (o.z + o.w);
             if (hi != nullptr) {
                 const float vv[4] = { o.x, o.y, o.z, o.w };
@@ -276,8 +276,9 @@ __global__ void __launch_bounds__(256) k_descriptor_head(const float* __restrict
     }
 }
 
-static int g_norm_v4 = 1;
+static int g_norm_v4 = 1, g_norm_variant = 0;
 void dense_set_norm_v4(int v) { g_norm_v4 = v; }
+void dense_set_norm_variant(int v) { g_norm_variant = v; }
 
 // ---- host side ---------------------------------------------------------------------------------
 int colstats_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, float eps, float* mean, float* rstd,
@@ -315,6 +316,7 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
 {
     if (n == 0) return PCRCG_OK;
     PCRCG_REQUIRE(split_hi == nullptr || (split_lo != nullptr && split_ld % 8 == 0 && split_ld >= C), "norm_act: bad split geometry");
+    PCRCG_REQUIRE(out != nullptr || split_hi != nullptr, "norm_act: no output requested (out and the split planes are both NULL)");
     ProfScope prof(PC_NORM, st, 1);
     if (C % 4 == 0 && n < (1ll << 31) && g_norm_v4) {
         const int c4 = C / 4;
@@ -322,9 +324,18 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
         const bool flag_ok = rowflag != nullptr && (c4 & (c4 - 1)) == 0;
         const int tcols = flag_ok ? (c4 < 32 ? c4 : 32) : (c4 < 256 ? c4 : 256), trows = 256 / tcols;
         PCRCG_REQUIRE(rowflag == nullptr || flag_ok, "norm_act: row flags need a power-of-two channel count");
-        k_norm_act_v4<<<(unsigned)cdiv64(n, trows * NA_UNROLL), 256, 0, st>>>(x, (int)n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd,
-                                                                           slope, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo,
-                                                                           split_ld, tcols, trows, rowflag);
+#define PCRCG_NA(U_, B_) k_norm_act_v4<U_, B_><<<(unsigned)cdiv64(n, trows * U_), 256, 0, st>>>( \
+            x, (int)n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, \
+            split_ld, tcols, trows, rowflag)
+        // launch shape measured per case on B200 (tools/bench_norm_apply.py): the row-flag mode (narrow tensors, extra shuffles)
+        // prefers more resident warps, the plain streaming mode more loads in flight per thread
+        switch (g_norm_variant > 0 ? g_norm_variant : (rowflag != nullptr ? 4 : 2)) {
+            case 1: PCRCG_NA(4, 3); break;
+            case 2: PCRCG_NA(8, 2); break;
+            case 4: PCRCG_NA(2, 4); break;
+            default: PCRCG_NA(4, 2); break;
+        }
+#undef PCRCG_NA
         PCRCG_CUDA(cudaGetLastError());
         return PCRCG_OK;
     }

@@ -803,6 +803,10 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     PCRCG_REQUIRE(kp_extent > 0.f, "kpconv: KP_extent must be positive");
     PCRCG_REQUIRE((unsigned long long)ns * (unsigned long long)cin < (1ull << 32), "kpconv: feature table too large for 32-bit offsets");
     if (nq == 0) return PCRCG_OK;
+    // x may be NULL when the features exist only as bf16 (hi, lo) planes with their row flags (a producer that skipped the fp32 copy)
+    PCRCG_REQUIRE(x != nullptr || (x_hi != nullptr && x_lo != nullptr && rowflag_in != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 &&
+                                   !g_agg_simt && !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, K * cin)),
+                  "kpconv: fp32 features are required on this path (planes-only input needs cin %% 64 == 0, row flags and the tensor-core path)");
     const int KC = K * cin;
     const bool tc = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC);
     PCRCG_REQUIRE(stats_acc == nullptr || tc, "kpconv: output statistics are produced by the tensor-core contraction only");

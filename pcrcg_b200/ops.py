@@ -134,7 +134,12 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
     stat_segments: False = plain; True / int32 row starts = also accumulate the InstanceNorm statistics of the
     result in the contraction epilogue (attached as ``out._pcrcg_stats`` for :func:`instance_norm_act`)."""
     _need_cuda(q_pts, s_pts, neighb_inds, x, kernel_points, weights)
-    q_pts, s_pts, x = _f32c(q_pts), _f32c(s_pts), _f32c(x)
+    planes = isinstance(x, PlaneTensor)
+    if planes and (_force_simt or x._pcrcg_rowpos is None or weights.shape[2] % 16 != 0 or stat_segments is False or not _fuse_stats):
+        x, planes = x.dense(), False            # paths that read the fp32 rows
+    q_pts, s_pts = _f32c(q_pts), _f32c(s_pts)
+    if not planes:
+        x = _f32c(x)
     kernel_points, weights = _f32c(kernel_points), _f32c(weights)
     idx, is64, H, stride = _idx(neighb_inds)
     nq, ns, cin = q_pts.shape[0], s_pts.shape[0], x.shape[1]
@@ -147,12 +152,15 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         ws = _ws(L.pcrcg_kpconv_ws_bytes(nq, ns, cin, K), dev)
         sp = getattr(x, "_pcrcg_split", None)
+        xptr = None if planes else x.data_ptr()
         seg, acc = _stats_begin(nq, cout, stat_segments, dev)
+        if planes and (acc is None or K * cin < 16):
+            raise RuntimeError("kpconv_forward: planes-only features need the tensor-core path")
         if acc is not None and K * cin >= 16:
             hi, lo, ld = sp if sp is not None else (None, None, 0)
             rp = getattr(x, "_pcrcg_rowpos", None) if sp is not None else None
             check(L.pcrcg_kpconv_forward_stats_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
-                                                   x.data_ptr(), hi.data_ptr() if hi is not None else None,
+                                                   xptr, hi.data_ptr() if hi is not None else None,
                                                    lo.data_ptr() if lo is not None else None, ld,
                                                    rp.data_ptr() if rp is not None else None, cin, kernel_points.data_ptr(), K,
                                                    float(KP_extent), weights.data_ptr(), cout, out.data_ptr(), ws.data_ptr(),
@@ -186,9 +194,14 @@ def linear(x, weight, stat_segments=False):
     If the producer of ``x`` attached its bf16 (hi, lo) planes (``x._pcrcg_split``) the tensor-core
     contraction consumes them directly.  stat_segments: see :func:`kpconv_forward`."""
     _need_cuda(x, weight)
-    x, weight = _f32c(x), _f32c(weight)
-    n, cin = x.shape
+    weight = _f32c(weight)
     cout = weight.shape[0]
+    if isinstance(x, PlaneTensor):
+        if _force_simt or cout % 16 != 0 or x.shape[1] < 16:
+            x = x.dense()
+    else:
+        x = _f32c(x)
+    n, cin = x.shape
     out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
     L = lib()
     sp = getattr(x, "_pcrcg_split", None)
@@ -240,6 +253,24 @@ def column_stats(x, segments=None, eps=1e-5):
     return mean, rstd, seg
 
 
+class PlaneTensor:
+    """Features that exist ONLY as bf16 (hi, lo) planes (x = hi + lo), produced by ``instance_norm_act(planes_only=True)``
+    for results consumed solely by tensor-core contractions (a ResnetBottleneck block's unary1 and KPConv-norm outputs):
+    the fp32 copy is never written.  Accepted by :func:`linear` and :func:`kpconv_forward`; ``dense()`` rebuilds fp32."""
+
+    def __init__(self, hi, lo, ld, n, c, rowpos=None):
+        self._pcrcg_split = (hi, lo, ld)
+        self._pcrcg_rowpos = rowpos
+        self.shape = (n, c)
+        self.device = hi.device
+        self.is_cuda = True
+        self.dtype = torch.float32
+
+    def dense(self):
+        hi, lo, _ = self._pcrcg_split
+        return (hi[:, :self.shape[1]].float() + lo[:, :self.shape[1]].float()).contiguous()
+
+
 def _stats_of(x, segments, eps):
     """statistics attached by the producing contraction (same eps, same segment tensor) or a pass over x"""
     st = getattr(x, "_pcrcg_stats", None)
@@ -251,7 +282,7 @@ def _stats_of(x, segments, eps):
 
 
 def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm=False, eps=1e-5, emit_split=False,
-                      emit_rowpos=False):
+                      emit_rowpos=False, planes_only=False):
     """act(IN(x) + [IN](shortcut)) with act = LeakyReLU(slope) or identity (slope=None).
     models/blocks.py:456-463 (+ :501, :590, :662, :678).  emit_split: also write the bf16 (hi, lo)
     planes of the result (attached as ``out._pcrcg_split``) for a following :func:`linear`."""
@@ -264,17 +295,21 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
         if shortcut_norm:
             scm, scr, _ = _stats_of(shortcut, segments, eps)
         shortcut = _f32c(shortcut)
-    out = torch.empty_like(x)
     p = lambda t: t.data_ptr() if t is not None else None
     sp = _split_planes(n, c, x.device) if (emit_split and c % 8 == 0 and not _force_simt) else None
     rp = None
     if emit_rowpos and sp is not None and c % 4 == 0 and ((c // 4) & (c // 4 - 1)) == 0:
         rp = torch.empty(n, dtype=torch.uint8, device=x.device)       # (row sum > 0) for the KPConv neighbour count
+    # planes_only: the consumer is a tensor-core contraction (c % 64 == 0 covers KPConv's plane kernel and the Linear)
+    planes_only = bool(planes_only and sp is not None and c % 64 == 0 and n >= 1 and (rp is not None or not emit_rowpos))
+    out = None if planes_only else torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
-                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), out.data_ptr(),
+                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), p(out),
                                        sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0,
                                        rp.data_ptr() if rp is not None else None, _stream()))
+    if planes_only:
+        return PlaneTensor(sp[0], sp[1], sp[2], n, c, rp)
     if sp is not None:
         out._pcrcg_split = sp
     if rp is not None:
