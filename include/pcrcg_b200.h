@@ -157,6 +157,30 @@ int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
 int pcrcg_descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency,
                               pcrcg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Bottleneck overlap-attention GNN ("next" row 3 of the scope table) -- models/gcn.py, models/architectures.py:528-565.
+ * Dense contractions of these layers use pcrcg_gemm_dev; these are the remaining operators.  cloud_starts [nb+1] int32
+ * device = row starts of the stacked clouds.
+ *   pcrcg_knn_dev            get_graph_feature's kNN (models/gcn.py:48-51): out [n,k] int32 global rows = the k+1 smallest
+ *                            of clamp(-2 x.y + |x|^2 + |y|^2, 1e-12) inside the query's cloud, first dropped; ties by index
+ *   pcrcg_edge_max_stats_dev 1x1 conv over the edge features [f_n ; f_j - f_n] (models/gcn.py:54-66,125-131) after the split
+ *                            W [f_n ; f_j - f_n] = u_n + v_j:  out [n,C] = u_n + max_j v[knn[n,j]]  and stats_acc
+ *                            [nb][2][C] fp64 += (sum, sum of squares)/k of u_n + v_j over all edges (InstanceNorm2d
+ *                            statistics; finish with pcrcg_colstats_final_dev, apply with pcrcg_norm_act_dev)
+ *   pcrcg_bias_act_dev       out = act(x + bias[c]) (Conv1d bias; slope < 0: identity, 0: ReLU, > 0: LeakyReLU); in place ok
+ *   pcrcg_softmax_rows_dev   x[r, 0:m] <- softmax(scale * x[r, 0:m])   (attention, models/gcn.py:153-157; saliency :561-563)
+ *   pcrcg_l2norm_rows_dev    out = x / max(|x|_2, eps) per row          (F.normalize, models/architectures.py:543)
+ * ------------------------------------------------------------------------------------------- */
+int pcrcg_knn_dev(const float* points, int64_t n, const int32_t* cloud_starts, int32_t nb, int32_t k, int32_t* out,
+                  pcrcg_stream_t stream);
+int pcrcg_edge_max_stats_dev(const float* u, int32_t ldu, const float* v, int32_t ldv, const int32_t* knn, int64_t n,
+                             int32_t C, int32_t k, const int32_t* cloud_starts, int32_t nb, float* out, double* stats_acc,
+                             pcrcg_stream_t stream);
+int pcrcg_bias_act_dev(const float* x, int64_t n, int32_t C, const float* bias, float slope, float* out,
+                       pcrcg_stream_t stream);
+int pcrcg_softmax_rows_dev(float* x, int64_t n, int32_t m, int32_t ld, float scale, pcrcg_stream_t stream);
+int pcrcg_l2norm_rows_dev(const float* x, int64_t n, int32_t C, float eps, float* out, pcrcg_stream_t stream);
+
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,
                        int32_t idx_stride, float* out, pcrcg_stream_t stream);

@@ -75,6 +75,13 @@ int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int3
 int descriptor_head_dev(const float*, int64_t, int32_t, float*, float*, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
+int knn_dev(const float*, int64_t, const int32_t*, int32_t, int32_t, int32_t*, cudaStream_t);
+int edge_max_stats_dev(const float*, int32_t, const float*, int32_t, const int32_t*, int64_t, int32_t, int32_t, const int32_t*, int32_t, float*,
+                       double*, cudaStream_t);
+int bias_act_dev(const float*, int64_t, int32_t, const float*, float, float*, cudaStream_t);
+int softmax_rows_dev(float*, int64_t, int32_t, int32_t, float, cudaStream_t);
+int l2norm_rows_dev(const float*, int64_t, int32_t, float, float*, cudaStream_t);
+
 size_t projection_ws_bytes(int64_t n);
 int projection_dev(const float*, int64_t, const float*, int32_t, int32_t, const float*, const float*, float, long long*, long long*, int32_t*,
                    void*, size_t, cudaStream_t);
@@ -317,6 +324,32 @@ int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* in
                            float* out, pcrcg_stream_t stream)
 {
     return closest_pool_dev(x, ns, C, inds, idx_is_i64, nq, idx_stride, out, (cudaStream_t)stream);
+}
+
+int pcrcg_knn_dev(const float* points, int64_t n, const int32_t* cloud_starts, int32_t nb, int32_t k, int32_t* out, pcrcg_stream_t stream)
+{
+    return knn_dev(points, n, cloud_starts, nb, k, out, (cudaStream_t)stream);
+}
+
+int pcrcg_edge_max_stats_dev(const float* u, int32_t ldu, const float* v, int32_t ldv, const int32_t* knn, int64_t n, int32_t C, int32_t k,
+                             const int32_t* cloud_starts, int32_t nb, float* out, double* stats_acc, pcrcg_stream_t stream)
+{
+    return edge_max_stats_dev(u, ldu, v, ldv, knn, n, C, k, cloud_starts, nb, out, stats_acc, (cudaStream_t)stream);
+}
+
+int pcrcg_bias_act_dev(const float* x, int64_t n, int32_t C, const float* bias, float slope, float* out, pcrcg_stream_t stream)
+{
+    return bias_act_dev(x, n, C, bias, slope, out, (cudaStream_t)stream);
+}
+
+int pcrcg_softmax_rows_dev(float* x, int64_t n, int32_t m, int32_t ld, float scale, pcrcg_stream_t stream)
+{
+    return softmax_rows_dev(x, n, m, ld, scale, (cudaStream_t)stream);
+}
+
+int pcrcg_l2norm_rows_dev(const float* x, int64_t n, int32_t C, float eps, float* out, pcrcg_stream_t stream)
+{
+    return l2norm_rows_dev(x, n, C, eps, out, (cudaStream_t)stream);
 }
 
 size_t pcrcg_projection_ws_bytes(int64_t n) { return projection_ws_bytes(n); }

@@ -374,3 +374,86 @@ def force_simt_contraction(on):
     global _force_simt
     _force_simt = bool(on)
     lib().pcrcg_gemm_force_simt(1 if on else 0)
+
+
+# =================================================================================================
+# Bottleneck GNN operators (models/gcn.py, models/architectures.py:528-565)
+# =================================================================================================
+def cloud_starts(lens):
+    """lens [B] (any int tensor / sequence) -> int32 device-agnostic row starts [B+1] (host computation: B is tiny)."""
+    l = torch.as_tensor(lens, dtype=torch.int64).cpu()
+    return torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(l, 0)]).to(torch.int32)
+
+
+def gemm(a, b, b_is_nk, out=None):
+    """a [M,K] @ (b [N,K]^T if b_is_nk else b [K,N]) -> [M,N].  2-D fp32 CUDA tensors whose LAST stride is 1; row strides
+    are passed through (column slices of wider matrices -- attention heads -- need no copy)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(1) == 1 and b.stride(1) == 1
+    m, k = a.shape
+    n = b.shape[0] if b_is_nk else b.shape[1]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    assert out.shape == (m, n) and out.stride(1) == 1
+    with torch.cuda.device(a.device):
+        check(lib().pcrcg_gemm_dev(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), 1 if b_is_nk else 0, out.data_ptr(), out.stride(0),
+                                   m, n, k, None, _stream()))
+    return out
+
+
+def knn(points, starts, k):
+    """models/gcn.py:48-51.  points [N,3], starts = cloud row starts [B+1] -> int32 [N,k] global rows."""
+    _need_cuda(points)
+    points = _f32c(points)
+    starts = _i32c(starts.to(points.device))
+    out = torch.empty((points.shape[0], k), dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib().pcrcg_knn_dev(points.data_ptr(), points.shape[0], starts.data_ptr(), starts.shape[0] - 1, int(k), out.data_ptr(), _stream()))
+    return out
+
+
+def edge_conv_max(uv, cout, knn_idx, starts, slope=0.2, eps=1e-5):
+    """uv [N, 2*cout] = (u | v) node-level halves of the edge convolution -> act(IN2d(u_n + v_j)) max-reduced over the k
+    edges [N, cout] (models/gcn.py:125-131), statistics per cloud."""
+    _need_cuda(uv, knn_idx)
+    n, k = knn_idx.shape
+    dev = uv.device
+    starts = _i32c(starts.to(dev))
+    nb = starts.shape[0] - 1
+    m = torch.empty((n, cout), dtype=torch.float32, device=dev)
+    acc = torch.zeros((nb, 2, cout), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().pcrcg_edge_max_stats_dev(uv.data_ptr(), uv.stride(0), uv.data_ptr() + 4 * cout, uv.stride(0), knn_idx.data_ptr(), n, cout, k,
+                                             starts.data_ptr(), nb, m.data_ptr(), acc.data_ptr(), _stream()))
+        _stats_end(m, starts, acc, eps)
+    return instance_norm_act(m, starts, slope, eps=eps)
+
+
+def bias_act(x, bias, slope=None, out=None):
+    """act(x + bias): Conv1d bias, slope None = identity, 0.0 = ReLU.  In place when out is x."""
+    _need_cuda(x, bias)
+    x = _f32c(x)
+    n, c = x.shape
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_bias_act_dev(x.data_ptr(), n, c, bias.data_ptr() if bias is not None else None,
+                                       -1.0 if slope is None else float(slope), out.data_ptr(), _stream()))
+    return out
+
+
+def softmax_rows_(x, scale=1.0):
+    """in place: x <- softmax(scale * x, dim=1)"""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_softmax_rows_dev(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), float(scale), _stream()))
+    return x
+
+
+def l2_normalize(x, eps=1e-12):
+    _need_cuda(x)
+    x = _f32c(x)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().pcrcg_l2norm_rows_dev(x.data_ptr(), x.shape[0], x.shape[1], float(eps), out.data_ptr(), _stream()))
+    return out

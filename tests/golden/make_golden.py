@@ -220,6 +220,47 @@ def main():
     np.savez_compressed(f"{OUT}/decoder_ref.npz", **gd)
     print("decoder out", x.shape)
 
+    # ---- bottleneck GNN: models/gcn.py:37-217, models/architectures.py:528-565 ---------
+    from models.gcn import GCN
+    gg = {}
+    torch.manual_seed(3); np.random.seed(3)
+    with torch.no_grad():
+        # (A) GCN alone, feature_dim 128 (4 heads x 32), on the level-2 clouds of the small pyramid (115 + 95 nodes)
+        c2 = torch.from_numpy(pyr["points"][2]); l2 = pyr["stack_lengths"][2]
+        gcn = GCN(4, 128, 10, ["self", "cross", "self"]).eval()
+        f = torch.randn(len(c2), 128)
+        c0, c1 = c2[:l2[0]], c2[l2[0]:]
+        d0, d1 = gcn(c0.unsqueeze(0).transpose(1, 2), c1.unsqueeze(0).transpose(1, 2),
+                     f[:l2[0]].t().unsqueeze(0), f[l2[0]:].t().unsqueeze(0))
+        gg["gcn_coords"], gg["gcn_lens"], gg["gcn_feats"] = c2.numpy(), np.asarray(l2, np.int32), f.numpy()
+        gg["gcn_out"] = torch.cat([d0, d1], dim=-1).squeeze(0).t().contiguous().numpy()
+        for k, v in gcn.state_dict().items():
+            gg["gcnsd_" + k] = v.numpy()
+        # the kNN lists the reference's get_graph_feature uses (models/gcn.py:48-51), per cloud, global row indices
+        from models.gcn import square_distance as sqd
+        knn = []
+        for cc, off in ((c0, 0), (c1, int(l2[0]))):
+            dist = sqd(cc.unsqueeze(0), cc.unsqueeze(0))
+            knn.append(dist.topk(k=11, dim=-1, largest=False, sorted=True)[1][0, :, 1:] + off)
+        gg["gcn_knn"] = torch.cat(knn).numpy().astype(np.int32)
+        # (B) the whole KPFCNN.forward (image_feature False) on the small pair: encoder -> bottle -> GNN -> decoder
+        cfg = indoor_cfg(first_feats_dim=32)
+        cfg.gnn_feats_dim = 64
+        torch.manual_seed(4); np.random.seed(4)
+        net = KPFCNN(cfg).eval()
+        net.epsilon.data.fill_(-2.0)
+        fb = dict(batch)
+        fb["features"] = torch.ones(len(pts), 1)
+        fb["src_pcd_raw"], fb["tgt_pcd_raw"] = torch.from_numpy(src), torch.from_numpy(tgt)
+        fb["stack_lengths"] = [torch.from_numpy(np.asarray(x, np.int32)) for x in pyr["stack_lengths"]]
+        res = net(fb)
+        gg["net_feats_f"] = res["feats_f"].numpy()
+        gg["net_scores_overlap"], gg["net_scores_saliency"] = res["scores_overlap"].numpy(), res["scores_saliency"].numpy()
+        for k, v in net.state_dict().items():
+            gg["netsd_" + k] = v.numpy()
+    np.savez_compressed(f"{OUT}/gnn_ref.npz", **gg)
+    print("gnn: gcn out", gg["gcn_out"].shape, "net feats", gg["net_feats_f"].shape)
+
     # ---- projection --------------------------------------------------------------------------
     from projection import Projection
     gp = {}

@@ -195,3 +195,33 @@ def test_decoder_port_vs_reference_golden(blk):
     feats, so, ss, raw = bp.decoder(_t(dec["bottleneck_x"]), skips[:3], batch, Ws, 32)
     assert _close(raw, dec["decoder_out"], 1e-4) and _close(feats, dec["feats_f"], 1e-4)
     assert _close(so, dec["scores_overlap"], 1e-4) and _close(ss, dec["scores_saliency"], 1e-4)
+
+
+# ---- bottleneck GNN + whole network ------------------------------------
+from oracle import gcn_port as gp  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gnn():
+    return np.load(os.path.join(G, "gnn_ref.npz"))
+
+
+def test_gcn_port_vs_reference_golden(gnn):
+    sd = {k[6:]: _t(gnn[k]) for k in gnn.files if k.startswith("gcnsd_")}
+    coords, lens, feats = _t(gnn["gcn_coords"]), gnn["gcn_lens"], _t(gnn["gcn_feats"])
+    assert np.array_equal(gp.knn_lists(coords, lens, 10).numpy(), gnn["gcn_knn"])
+    out = gp.gcn(coords, lens, feats, sd, ["self", "cross", "self"], 4, 10)
+    assert _close(out, gnn["gcn_out"], 1e-4)
+
+
+def test_whole_network_port_vs_reference_golden(blk, gnn):
+    """encoder -> bottle -> GNN -> saliency -> decoder, every stage from the oracle ports, vs KPFCNN.forward of the reference"""
+    sd = {k[6:]: _t(gnn[k]) for k in gnn.files if k.startswith("netsd_")}
+    blocks = bp.encoder_blocks_from_state_dict(sd, prefix="encoder_blocks.")
+    batch = {k: [_t(blk[f"{k}_{l}"]) for l in range(4)] for k in ("points", "neighbors", "pools", "upsamples")}
+    x, outs = bp.encoder(torch.ones(batch["points"][0].shape[0], 1), batch, blocks)
+    xb = gp.bottleneck(x, batch["points"][3], blk["stack_lengths_3"], sd, ["self", "cross", "self"], 4, 10)
+    Ws = [sd["decoder_blocks.1.mlp.weight"], sd["decoder_blocks.3.mlp.weight"], sd["decoder_blocks.5.mlp.weight"]]
+    feats, so, ss, _ = bp.decoder(xb, [outs[1], outs[4], outs[7]], batch, Ws, 32)
+    assert _close(feats, gnn["net_feats_f"], 1e-3)
+    assert _close(so, gnn["net_scores_overlap"], 1e-3) and _close(ss, gnn["net_scores_saliency"], 1e-3)
