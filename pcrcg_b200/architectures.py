@@ -21,7 +21,7 @@ from .gcn import GCN, _Conv
 class KPFCNN(nn.Module):
     def __init__(self, config):
         super().__init__()
-        if getattr(config, "node_overlap", False) or getattr(config, "quaternion", False):
+        if dict.get(config, "node_overlap", False) or dict.get(config, "quaternion", False):
             raise NotImplementedError("pcrcg_b200.KPFCNN: the node_overlap / quaternion training heads are not built")
         enc = KPEncoder(config)
         self.encoder_blocks = enc.encoder_blocks

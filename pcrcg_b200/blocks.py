@@ -254,14 +254,15 @@ def indoor_config(**over):
     c = Config(num_layers=4, in_points_dim=3, first_feats_dim=256, final_feats_dim=32, first_subsampling_dl=0.025,
                in_feats_dim=1, conv_radius=2.5, deform_radius=5.0, num_kernel_points=15, KP_extent=2.0, KP_influence="linear",
                aggregation_mode="sum", fixed_kernel_points="center", use_batch_norm=True, batch_norm_momentum=0.02,
-               deformable=False, modulated=False, architecture=ARCHITECTURES["indoor"])
+               deformable=False, modulated=False, architecture=ARCHITECTURES["indoor"],
+               gnn_feats_dim=512, dgcnn_k=10, num_head=4, nets=["self", "cross", "self"])      # configs/test/indoor.yaml:31,48-50
     c.update(over)
     return c
 
 
 def kitti_config(**over):
     """configs/test/kitti.yaml:10-27"""
-    return indoor_config(**{**dict(first_subsampling_dl=0.3, conv_radius=4.25), **over})
+    return indoor_config(**{**dict(first_subsampling_dl=0.3, conv_radius=4.25, gnn_feats_dim=256), **over})
 
 
 class KPEncoder(nn.Module):

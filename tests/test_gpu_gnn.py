@@ -136,3 +136,31 @@ def test_whole_network_vs_reference_golden(blk, gnn):
     assert _err(res["feats_f"], gnn["net_feats_f"]) < TOL
     assert _err(res["scores_overlap"], gnn["net_scores_overlap"]) < TOL
     assert _err(res["scores_saliency"], gnn["net_scores_saliency"]) < TOL
+
+
+def test_whole_network_stacked_pairs_equal_single_pairs():
+    """descriptors of a pair do not depend on what else is stacked in the batch (per-pair statistics, per-pair attention)"""
+    cfg = blocks.indoor_config(first_feats_dim=32, gnn_feats_dim=64)
+    limits = [30, 28, 28, 30]
+    torch.manual_seed(0)
+    net = architectures.KPFCNN(cfg).to(DEV)
+    for m in net.modules():
+        if isinstance(m, blocks.KPConv):
+            m.set_kernel_points(torch.randn(15, 3) * 0.4 * m.radius)
+    pairs = [synthetic.match3d_pair(s, n_target=1500 + 200 * s)[:2] for s in range(2)]
+    singles = []
+    for src, tgt in pairs:
+        b = dataloader.build_pyramid(np.concatenate([src, tgt]), np.array([len(src), len(tgt)], np.int32), cfg, limits, device=DEV)
+        b["features"] = torch.ones(len(src) + len(tgt), 1, device=DEV)
+        singles.append({k: v.cpu().numpy() for k, v in net(b).items()})
+    pts = np.concatenate([np.concatenate(p) for p in pairs])
+    lens = np.array([len(c) for p in pairs for c in p], np.int32)
+    b = dataloader.build_pyramid(pts, lens, cfg, limits, device=DEV)
+    b["features"] = torch.ones(len(pts), 1, device=DEV)
+    res = {k: v.cpu().numpy() for k, v in net(b).items()}
+    seg = b["pair_segments"][0].cpu().numpy()
+    for k, s in enumerate(singles):
+        for name in ("feats_f", "scores_overlap", "scores_saliency"):
+            part = res[name][seg[k]:seg[k + 1]]
+            assert part.shape == s[name].shape
+            assert np.abs(part - s[name]).max() <= 5e-4 * max(np.abs(s[name]).max(), 1e-6), name
