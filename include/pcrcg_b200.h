@@ -181,6 +181,17 @@ int pcrcg_bias_act_dev(const float* x, int64_t n, int32_t C, const float* bias, 
 int pcrcg_softmax_rows_dev(float* x, int64_t n, int32_t m, int32_t ld, float scale, pcrcg_stream_t stream);
 int pcrcg_l2norm_rows_dev(const float* x, int64_t n, int32_t C, float eps, float* out, pcrcg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Descriptor matching front-end ("next" row 4) -- lib/benchmark_utils.py:187-224,246-262,270-295.
+ *   pcrcg_best_match_dev   best_idx[i] = argmax_j <a[i,:], b[j,:]> (first maximum, as np.argmax / torch.max), best_val[i]
+ *                          (may be NULL) its score; a [n,D], b [m,D] row-major, D in {16,32,64}.  The [n,m] score matrix
+ *                          the reference builds is never materialised.
+ *   pcrcg_mutual_dev       mutual[i] = (col_best[row_best[i]] == i): mutual_selection's {0,1} matrix in sparse form
+ * ------------------------------------------------------------------------------------------- */
+int pcrcg_best_match_dev(const float* a, int64_t n, const float* b, int64_t m, int32_t D, int32_t* best_idx, float* best_val,
+                         pcrcg_stream_t stream);
+int pcrcg_mutual_dev(const int32_t* row_best, const int32_t* col_best, int64_t n, uint8_t* mutual, pcrcg_stream_t stream);
+
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,
                        int32_t idx_stride, float* out, pcrcg_stream_t stream);

@@ -82,6 +82,9 @@ int bias_act_dev(const float*, int64_t, int32_t, const float*, float, float*, cu
 int softmax_rows_dev(float*, int64_t, int32_t, int32_t, float, cudaStream_t);
 int l2norm_rows_dev(const float*, int64_t, int32_t, float, float*, cudaStream_t);
 
+int best_match_dev(const float*, int64_t, const float*, int64_t, int32_t, int32_t*, float*, cudaStream_t);
+int mutual_dev(const int32_t*, const int32_t*, int64_t, uint8_t*, cudaStream_t);
+
 size_t projection_ws_bytes(int64_t n);
 int projection_dev(const float*, int64_t, const float*, int32_t, int32_t, const float*, const float*, float, long long*, long long*, int32_t*,
                    void*, size_t, cudaStream_t);
@@ -350,6 +353,17 @@ int pcrcg_softmax_rows_dev(float* x, int64_t n, int32_t m, int32_t ld, float sca
 int pcrcg_l2norm_rows_dev(const float* x, int64_t n, int32_t C, float eps, float* out, pcrcg_stream_t stream)
 {
     return l2norm_rows_dev(x, n, C, eps, out, (cudaStream_t)stream);
+}
+
+int pcrcg_best_match_dev(const float* a, int64_t n, const float* b, int64_t m, int32_t D, int32_t* best_idx, float* best_val,
+                         pcrcg_stream_t stream)
+{
+    return best_match_dev(a, n, b, m, D, best_idx, best_val, (cudaStream_t)stream);
+}
+
+int pcrcg_mutual_dev(const int32_t* row_best, const int32_t* col_best, int64_t n, uint8_t* mutual, pcrcg_stream_t stream)
+{
+    return mutual_dev(row_best, col_best, n, mutual, (cudaStream_t)stream);
 }
 
 size_t pcrcg_projection_ws_bytes(int64_t n) { return projection_ws_bytes(n); }
