@@ -178,6 +178,15 @@ int pcrcg_edge_max_stats_dev(const float* u, int32_t ldu, const float* v, int32_
                              pcrcg_stream_t stream);
 int pcrcg_bias_act_dev(const float* x, int64_t n, int32_t C, const float* bias, float slope, float* out,
                        pcrcg_stream_t stream);
+/* point2node / node visibility of the collate ("next" row 1; datasets/dataloader.py:91-106, 133-158, 309-322):
+ *   out[i] = nearest node of point i inside its cloud (index LOCAL to the cloud's nodes; expanded squared distance of
+ *   datasets/dataloader.py:70-90, ties by node index);  total / visible_count [n_nodes] int32 (zeroed by the caller) +=
+ *   number of points assigned to each node / of those with visible[i] != 0. */
+int pcrcg_point2node_dev(const float* points, int64_t n, const int32_t* point_starts, const float* nodes,
+                         const int32_t* node_starts, int32_t nb, int32_t* out, pcrcg_stream_t stream);
+int pcrcg_node_counts_dev(const int32_t* point2node, const uint8_t* visible, int64_t n, const int32_t* point_starts,
+                          const int32_t* node_starts, int32_t nb, int32_t* total, int32_t* visible_count,
+                          pcrcg_stream_t stream);
 int pcrcg_softmax_rows_dev(float* x, int64_t n, int32_t m, int32_t ld, float scale, pcrcg_stream_t stream);
 int pcrcg_l2norm_rows_dev(const float* x, int64_t n, int32_t C, float eps, float* out, pcrcg_stream_t stream);
 

@@ -110,3 +110,22 @@ def bottleneck(x, coords_c, lens_c, sd, names, num_heads, k):
     s1 = torch.softmax(inner / temperature, dim=1) @ scores[n0:]
     s2 = torch.softmax(inner.t() / temperature, dim=1) @ scores[:n0]
     return torch.cat([scores, torch.cat([s1, s2]), f], dim=1)
+
+
+# ---- node labels of the collate (datasets/dataloader.py:91-198) --------------------------------------------------------
+def point2node(nodes, points):
+    """datasets/dataloader.py:91-106 (square_distance :70-90 is the same expanded form as models/gcn.py)."""
+    return square_distance(points, nodes).topk(k=1, dim=-1, largest=False)[1].squeeze(-1)
+
+
+def point2node_correspondences(src_nodes, src_points, tgt_nodes, tgt_points, corr):
+    """datasets/dataloader.py:108-198: visible fraction per node and the point -> node assignment."""
+    out = []
+    for nodes, pts, col in ((src_nodes, src_points, 0), (tgt_nodes, tgt_points, 1)):
+        idx = point2node(nodes, pts)
+        visible = torch.zeros(pts.shape[0], dtype=torch.bool)
+        visible[corr[:, col]] = True
+        tot = torch.bincount(idx, minlength=nodes.shape[0]).float()
+        vis = torch.bincount(idx[visible], minlength=nodes.shape[0]).float()
+        out.append((vis / torch.where(tot > 0, tot, torch.ones_like(tot)), idx))
+    return out[0][0], out[1][0], out[0][1], out[1][1]

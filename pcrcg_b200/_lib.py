@@ -59,6 +59,8 @@ SIGNATURES = {
     "pcrcg_l2norm_rows_dev": (C.c_int, [_P, _I64, _I32, _F, _P, _P]),
     "pcrcg_best_match_dev": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P, _P]),
     "pcrcg_mutual_dev": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "pcrcg_point2node_dev": (C.c_int, [_P, _I64, _P, _P, _P, _I32, _P, _P]),
+    "pcrcg_node_counts_dev": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _P, _P, _P]),
     "pcrcg_closest_pool_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _I64, _I32, _P, _P]),
 }
 

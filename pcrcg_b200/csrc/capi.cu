@@ -79,6 +79,8 @@ int knn_dev(const float*, int64_t, const int32_t*, int32_t, int32_t, int32_t*, c
 int edge_max_stats_dev(const float*, int32_t, const float*, int32_t, const int32_t*, int64_t, int32_t, int32_t, const int32_t*, int32_t, float*,
                        double*, cudaStream_t);
 int bias_act_dev(const float*, int64_t, int32_t, const float*, float, float*, cudaStream_t);
+int point2node_dev(const float*, int64_t, const int32_t*, const float*, const int32_t*, int32_t, int32_t*, cudaStream_t);
+int node_counts_dev(const int32_t*, const uint8_t*, int64_t, const int32_t*, const int32_t*, int32_t, int32_t*, int32_t*, cudaStream_t);
 int softmax_rows_dev(float*, int64_t, int32_t, int32_t, float, cudaStream_t);
 int l2norm_rows_dev(const float*, int64_t, int32_t, float, float*, cudaStream_t);
 
@@ -338,6 +340,18 @@ int pcrcg_edge_max_stats_dev(const float* u, int32_t ldu, const float* v, int32_
                              const int32_t* cloud_starts, int32_t nb, float* out, double* stats_acc, pcrcg_stream_t stream)
 {
     return edge_max_stats_dev(u, ldu, v, ldv, knn, n, C, k, cloud_starts, nb, out, stats_acc, (cudaStream_t)stream);
+}
+
+int pcrcg_point2node_dev(const float* points, int64_t n, const int32_t* point_starts, const float* nodes, const int32_t* node_starts, int32_t nb,
+                         int32_t* out, pcrcg_stream_t stream)
+{
+    return point2node_dev(points, n, point_starts, nodes, node_starts, nb, out, (cudaStream_t)stream);
+}
+
+int pcrcg_node_counts_dev(const int32_t* point2node, const uint8_t* visible, int64_t n, const int32_t* point_starts,
+                          const int32_t* node_starts, int32_t nb, int32_t* total, int32_t* visible_count, pcrcg_stream_t stream)
+{
+    return node_counts_dev(point2node, visible, n, point_starts, node_starts, nb, total, visible_count, (cudaStream_t)stream);
 }
 
 int pcrcg_bias_act_dev(const float* x, int64_t n, int32_t C, const float* bias, float slope, float* out, pcrcg_stream_t stream)

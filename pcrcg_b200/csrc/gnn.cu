@@ -65,6 +65,49 @@ __global__ void __launch_bounds__(256) k_knn_brute(const float* __restrict__ pts
     }
 }
 
+// ---- point2node (datasets/dataloader.py:91-106) ----------------------------------------------------
+// idx[i] = nearest NODE of point i inside its own cloud, under the reference's expanded squared distance
+// (datasets/dataloader.py:70-90: same formula as models/gcn.py) and topk(k=1, largest=False); ties by node index.
+// One warp per point; lanes stride the nodes of the cloud.  Returned indices are LOCAL to the cloud's node list, as in the
+// reference (which is called once per cloud).
+__global__ void __launch_bounds__(256) k_point2node(const float* __restrict__ pts, int n, const int32_t* __restrict__ pstarts,
+                                                    const float* __restrict__ nodes, const int32_t* __restrict__ nstarts, int nb,
+                                                    int32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int c = cloud_of(pstarts, nb, i);
+    const int s0 = nstarts[c], s1 = nstarts[c + 1];
+    const float qx = pts[3 * (size_t)i], qy = pts[3 * (size_t)i + 1], qz = pts[3 * (size_t)i + 2];
+    const float qn = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+    unsigned long long best = ~0ull;
+    for (int j = s0 + lane; j < s1; j += 32) {
+        const float d = knn_dist(qx, qy, qz, qn, nodes + 3 * (size_t)j);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(j - s0);
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, s);
+        best = x < best ? x : best;
+    }
+    if (lane == 0) out[i] = best == ~0ull ? 0 : (int32_t)(uint32_t)(best & 0xffffffffull);
+}
+
+// per node: number of points assigned to it and number of those flagged visible (datasets/dataloader.py:133-158)
+__global__ void __launch_bounds__(256) k_node_counts(const int32_t* __restrict__ p2n, const uint8_t* __restrict__ visible, int n,
+                                                     const int32_t* __restrict__ pstarts, const int32_t* __restrict__ nstarts, int nb,
+                                                     int32_t* __restrict__ tot, int32_t* __restrict__ vis)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cloud_of(pstarts, nb, i);
+    const int node = nstarts[c] + p2n[i];
+    atomicAdd(tot + node, 1);
+    if (visible[i]) atomicAdd(vis + node, 1);
+}
+
 // ---- edge max + statistics -----------------------------------------------------------------------
 // One warp per node; lanes stride the channels.  m[n,c] = u[n,c] + max_j v[idx[n,j],c]; per (cloud, channel) the sum and
 // the sum of squares of u[n,c] + v[idx[n,j],c] over all k edges, divided by k (so that the finaliser, which divides by
@@ -168,6 +211,28 @@ int knn_dev(const float* pts, int64_t n, const int32_t* cloud_starts, int32_t nb
     if (n == 0) return PCRCG_OK;
     ProfScope prof(PC_RADIUS_QUERY, st, 1);
     k_knn_brute<<<(unsigned)cdiv64(n, 8), 256, 0, st>>>(pts, (int)n, cloud_starts, nb, k, out);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+int point2node_dev(const float* pts, int64_t n, const int32_t* pstarts, const float* nodes, const int32_t* nstarts, int32_t nb, int32_t* out,
+                   cudaStream_t st)
+{
+    PCRCG_REQUIRE(n >= 0 && n < (1ll << 31) && nb >= 1, "point2node: bad dimensions");
+    if (n == 0) return PCRCG_OK;
+    ProfScope prof(PC_RADIUS_QUERY, st, 1);
+    k_point2node<<<(unsigned)cdiv64(n, 8), 256, 0, st>>>(pts, (int)n, pstarts, nodes, nstarts, nb, out);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+int node_counts_dev(const int32_t* p2n, const uint8_t* visible, int64_t n, const int32_t* pstarts, const int32_t* nstarts, int32_t nb,
+                    int32_t* tot, int32_t* vis, cudaStream_t st)
+{
+    PCRCG_REQUIRE(n >= 0 && n < (1ll << 31) && nb >= 1, "node_counts: bad dimensions");
+    if (n == 0) return PCRCG_OK;
+    ProfScope prof(PC_POOL, st, 1);
+    k_node_counts<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(p2n, visible, (int)n, pstarts, nstarts, nb, tot, vis);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

@@ -160,3 +160,45 @@ def calibrate_neighbors(pair_iter, config, keep_ratio=0.8, samples_threshold=200
             break
     cumsum = np.cumsum(neighb_hists.T, axis=0)
     return np.sum(cumsum < (keep_ratio * cumsum[hist_n - 1, :]), axis=0)
+
+
+# ---- node labels of the collate (datasets/dataloader.py:91-198, 309-322) -----------------------------------------------
+def _p2n(nodes, node_lens, points, point_lens):
+    dev = points.device
+    ps, ns = ops.cloud_starts(point_lens).to(dev), ops.cloud_starts(node_lens).to(dev)
+    out = torch.empty(points.shape[0], dtype=torch.int32, device=dev)
+    from ._lib import lib, check
+    with torch.cuda.device(dev):
+        check(lib().pcrcg_point2node_dev(points.data_ptr(), points.shape[0], ps.data_ptr(), nodes.data_ptr(), ns.data_ptr(),
+                                         ns.shape[0] - 1, out.data_ptr(), ops._stream()))
+    return out, ps, ns
+
+
+def point2node(nodes, points):
+    """datasets/dataloader.py:91-106: index [N] (int64) of the nearest node of every point (one cloud)."""
+    nodes = _dev_f32(nodes, nodes.device if torch.is_tensor(nodes) and nodes.is_cuda else "cuda")
+    points = _dev_f32(points, nodes.device)
+    out, _, _ = _p2n(nodes.contiguous(), [nodes.shape[0]], points.contiguous(), [points.shape[0]])
+    return out.long()
+
+
+def point2node_correspondences(src_nodes, src_points, tgt_nodes, tgt_points, point_correspondences, device=None):
+    """datasets/dataloader.py:108-198 -> (src_node_vis, tgt_node_vis, src_idx, tgt_idx): per node the fraction of its
+    points that have a ground-truth correspondence (nodes without points: 0 / 1), and the point -> node assignment."""
+    dev = src_nodes.device if torch.is_tensor(src_nodes) and src_nodes.is_cuda else torch.device("cuda")
+    sn, sp, tn, tp = (_dev_f32(t, dev).contiguous() for t in (src_nodes, src_points, tgt_nodes, tgt_points))
+    corr = torch.as_tensor(point_correspondences).to(dev).long()
+    nodes, pts = torch.cat([sn, tn]), torch.cat([sp, tp])
+    p2n, ps, ns = _p2n(nodes, [sn.shape[0], tn.shape[0]], pts, [sp.shape[0], tp.shape[0]])
+    visible = torch.zeros(pts.shape[0], dtype=torch.uint8, device=dev)
+    visible[corr[:, 0]] = 1
+    visible[corr[:, 1] + sp.shape[0]] = 1
+    tot = torch.zeros(nodes.shape[0], dtype=torch.int32, device=dev)
+    vis = torch.zeros(nodes.shape[0], dtype=torch.int32, device=dev)
+    from ._lib import lib, check
+    with torch.cuda.device(dev):
+        check(lib().pcrcg_node_counts_dev(p2n.data_ptr(), visible.data_ptr(), pts.shape[0], ps.data_ptr(), ns.data_ptr(), 2,
+                                          tot.data_ptr(), vis.data_ptr(), ops._stream()))
+    ratio = vis.float() / tot.clamp_min(1).float()                     # src_tot_num defaults to 1 (:135,148)
+    n_s, n_p = sn.shape[0], sp.shape[0]
+    return ratio[:n_s], ratio[n_s:], p2n[:n_p].long(), p2n[n_p:].long()

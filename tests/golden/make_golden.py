@@ -261,6 +261,29 @@ def main():
     np.savez_compressed(f"{OUT}/gnn_ref.npz", **gg)
     print("gnn: gcn out", gg["gcn_out"].shape, "net feats", gg["net_feats_f"].shape)
 
+    # ---- point2node / node visibility (datasets/dataloader.py:70-198) ------------------
+    # datasets/dataloader.py cannot be imported (it loads the cp37 cpp_wrappers binaries): the three pure-torch
+    # functions are taken from its SOURCE with ast and executed unchanged.
+    import ast
+    src_text = open(f"{REF}/datasets/dataloader.py").read()
+    tree = ast.parse(src_text)
+    wanted = ("square_distance", "point2node", "point2node_correspondences")
+    ns = {"torch": torch, "np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "dataloader.py", "exec"), ns)
+    gn = {}
+    rng = np.random.default_rng(7)
+    s_nodes, t_nodes = pyr["points"][3][:pyr["stack_lengths"][3][0]], pyr["points"][3][pyr["stack_lengths"][3][0]:]
+    corr = np.stack([rng.integers(0, len(src), 900), rng.integers(0, len(tgt), 900)], 1)
+    with torch.no_grad():
+        sv, tv, si, ti = ns["point2node_correspondences"](torch.from_numpy(s_nodes), torch.from_numpy(src), torch.from_numpy(t_nodes),
+                                                           torch.from_numpy(tgt), torch.from_numpy(corr))
+    gn.update(src_nodes=s_nodes, tgt_nodes=t_nodes, src_points=src, tgt_points=tgt, corr=corr, src_node_vis=sv.numpy(),
+              tgt_node_vis=tv.numpy(), src_idx=si.numpy(), tgt_idx=ti.numpy())
+    np.savez_compressed(f"{OUT}/point2node_ref.npz", **gn)
+    print("point2node: nodes", len(s_nodes), len(t_nodes), "vis mean", float(sv.mean()), float(tv.mean()))
+
     # ---- projection --------------------------------------------------------------------------
     from projection import Projection
     gp = {}

@@ -164,3 +164,13 @@ def test_whole_network_stacked_pairs_equal_single_pairs():
             part = res[name][seg[k]:seg[k + 1]]
             assert part.shape == s[name].shape
             assert np.abs(part - s[name]).max() <= 5e-4 * max(np.abs(s[name]).max(), 1e-6), name
+
+
+def test_point2node_and_node_visibility_vs_reference_golden():
+    """'next' row 1 (second half): datasets/dataloader.py:91-198 -- assignment exact, visibility ratios exact"""
+    g = np.load(os.path.join(G, "point2node_ref.npz"))
+    sv, tv, si, ti = dataloader.point2node_correspondences(_d(g["src_nodes"]), _d(g["src_points"]), _d(g["tgt_nodes"]), _d(g["tgt_points"]),
+                                                           torch.from_numpy(g["corr"]))
+    assert si.dtype == torch.int64 and np.array_equal(si.cpu().numpy(), g["src_idx"]) and np.array_equal(ti.cpu().numpy(), g["tgt_idx"])
+    assert np.array_equal(sv.cpu().numpy(), g["src_node_vis"]) and np.array_equal(tv.cpu().numpy(), g["tgt_node_vis"])
+    assert np.array_equal(dataloader.point2node(_d(g["src_nodes"]), _d(g["src_points"])).cpu().numpy(), g["src_idx"])

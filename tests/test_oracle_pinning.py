@@ -225,3 +225,11 @@ def test_whole_network_port_vs_reference_golden(blk, gnn):
     feats, so, ss, _ = bp.decoder(xb, [outs[1], outs[4], outs[7]], batch, Ws, 32)
     assert _close(feats, gnn["net_feats_f"], 1e-3)
     assert _close(so, gnn["net_scores_overlap"], 1e-3) and _close(ss, gnn["net_scores_saliency"], 1e-3)
+
+
+def test_point2node_port_vs_reference_golden():
+    g = np.load(os.path.join(G, "point2node_ref.npz"))
+    sv, tv, si, ti = gp.point2node_correspondences(_t(g["src_nodes"]), _t(g["src_points"]), _t(g["tgt_nodes"]), _t(g["tgt_points"]),
+                                                   torch.from_numpy(g["corr"]))
+    assert np.array_equal(si.numpy(), g["src_idx"]) and np.array_equal(ti.numpy(), g["tgt_idx"])
+    assert np.array_equal(sv.numpy(), g["src_node_vis"]) and np.array_equal(tv.numpy(), g["tgt_node_vis"])
