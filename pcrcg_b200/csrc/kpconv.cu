@@ -546,15 +546,16 @@ __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t
 {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-// packs (lo half = a, hi half = b) as bf16x2 and returns the residuals
+// Splits two fp32 values into packed bf16 (hi, lo) pairs (low half = a, high half = b) WITHOUT conversion instructions:
+// hi = the upper 16 bits of the float (truncation), lo = the upper 16 bits of the exact residual x - hi.  hi + lo keeps
+// >= 15 mantissa bits (error <= 2^-16 |x|, of the same order as the lo*lo term bf16x3 drops); PRMT / LOP3 / FADD run on the
+// full-rate pipes where F2F (one per value and rounding step, 112 per point before) is quarter-rate.
 __device__ __forceinline__ uint32_t pack_split(float a, float b, uint32_t& lo_packed)
 {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                    // one packed conversion (.x = a in the low half)
-    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
-    const float ha = __uint_as_float(hu << 16), hb = __uint_as_float(hu & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
-    lo_packed = *reinterpret_cast<const uint32_t*>(&l);
-    return hu;
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
+    lo_packed = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+    return __byte_perm(ua, ub, 0x7632);
 }
 
 template <typename IdxT>
@@ -649,8 +650,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
             for (int e = 0; e < 4; e++) {
                 const int rn = 16 * s + 2 * t + (e & 1) + (e >> 1) * 8;
                 const float4 p = *reinterpret_cast<const float4*>(s_xyz + rn * 4);
-                const float d0 = fmaxf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))), 0.f);
-                const float d1 = fmaxf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))), 0.f);
+                // the expanded squared distance can come out slightly negative next to a kernel point: |.| (a free operand
+                // modifier) instead of a max keeps the square root defined; the error is the same few ulps of |p'|^2
+                const float d0 = fabsf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))));
+                const float d1 = fabsf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))));
                 wv[0][e] = fmaxf(0.f, fmaf(-sqrt_approx(d0), inv_extent, 1.f));
                 wv[1][e] = fmaxf(0.f, fmaf(-sqrt_approx(d1), inv_extent, 1.f));
             }
