@@ -126,6 +126,7 @@ int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* 
 /* 1: force the fp32 CUDA-core contraction (parity anchor); 0: tcgen05 tensor-core path where shapes allow. */
 void pcrcg_gemm_force_simt(int32_t on);
 /* A/B switches for measurements: "contraction_simt", "aggregate_simt" (CUDA-core variants of the two KPConv stages),
+ * "aggregate_pipelined" (persistent software-pipelined bf16 aggregation, default 1; 0 = one point per warp),
  * "norm_vectorised" (float4 InstanceNorm apply kernel, default 1). */
 int pcrcg_set_option(const char* name, int32_t value);
 

@@ -100,6 +100,16 @@ __device__ __forceinline__ int cloud_of(const int32_t* __restrict__ starts, int 
     return lo;
 }
 
+// Order of the 64 channels of a slab inside the KPConv intermediate when the pipelined aggregation produces it: channel
+// c = 8*nt + 2*t + e (accumulator tile nt of mma.m16n8k16, thread column t, element e) is stored at
+// 32*(nt>>2) + 8*t + 2*(nt&3) + e, so a thread's four tiles form 16 contiguous bytes and the four threads of a row 64.
+// The contraction weights are split with the same permutation of their K index (gemm_tc.cu), so the product is unchanged.
+__host__ __device__ __forceinline__ int kperm64(int c)
+{
+    const int nt = c >> 3, t = (c >> 1) & 3, e = c & 1;
+    return ((nt >> 2) << 5) | (t << 3) | ((nt & 3) << 1) | e;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;

@@ -386,9 +386,11 @@ __global__ void __launch_bounds__(256) k_split_bf16(const float* __restrict__ x,
     *reinterpret_cast<uint2*>(lo + (size_t)r * ldo + c) = *reinterpret_cast<uint2*>(l);
 }
 
-// B given as [K,N] row-major -> hi/lo [N, ldo] (K contiguous), via a 32x32 shared-memory transpose
+// B given as [K,N] row-major -> hi/lo [N, ldo] (K contiguous), via a 32x32 shared-memory transpose.
+// perm64: the K index is permuted inside every aligned block of 64 (common.cuh: kperm64) -- the order in which the
+// pipelined KPConv aggregation writes its 64-channel slabs (one thread's accumulator fragments become contiguous).
 __global__ void __launch_bounds__(256) k_split_bf16_transpose(const float* __restrict__ B, int ldb, int K, int N, __nv_bfloat16* __restrict__ hi,
-                                                              __nv_bfloat16* __restrict__ lo, int ldo)
+                                                              __nv_bfloat16* __restrict__ lo, int ldo, int perm64)
 {
     __shared__ float t[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
@@ -402,9 +404,10 @@ __global__ void __launch_bounds__(256) k_split_bf16_transpose(const float* __res
         int n = n0 + j, k = k0 + tx;
         if (n < N && k < ldo) {
             float v = k < K ? t[tx][j] : 0.f;
+            const int kk = perm64 ? ((k & ~63) | kperm64(k & 63)) : k;
             __nv_bfloat16 h = __float2bfloat16_rn(v);
-            hi[(size_t)n * ldo + k] = h;
-            lo[(size_t)n * ldo + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+            hi[(size_t)n * ldo + kk] = h;
+            lo[(size_t)n * ldo + kk] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
     }
 }
@@ -492,8 +495,15 @@ int split_bf16_dev(const float* x, int ldx, int64_t rows, int cols, void* hi, vo
 }
 
 // Split (and transpose if needed) the fp32 B operand into bf16 hi/lo [N, ldk] (K contiguous).
+int gemm_tc_split_b_perm_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi_v, void* b_lo_v, int perm64, cudaStream_t st);
 int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi_v, void* b_lo_v, cudaStream_t st)
 {
+    return gemm_tc_split_b_perm_dev(B, ldb, b_is_nk, N, K, ldk, b_hi_v, b_lo_v, 0, st);
+}
+
+int gemm_tc_split_b_perm_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi_v, void* b_lo_v, int perm64, cudaStream_t st)
+{
+    PCRCG_REQUIRE(!perm64 || (!b_is_nk && K % 64 == 0), "gemm_tc: the permuted split needs a [K,N] operand with K %% 64 == 0");
     __nv_bfloat16* b_hi = (__nv_bfloat16*)b_hi_v;
     __nv_bfloat16* b_lo = (__nv_bfloat16*)b_lo_v;
     count_launches(1);
@@ -501,7 +511,7 @@ int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int 
         long long tot = (long long)N * (ldk / 4);
         k_split_bf16<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, N, K, b_hi, b_lo, ldk);
     } else {
-        k_split_bf16_transpose<<<dim3((unsigned)cdiv64(ldk, 32), (unsigned)cdiv64(N, 32)), 256, 0, st>>>(B, ldb, K, N, b_hi, b_lo, ldk);
+        k_split_bf16_transpose<<<dim3((unsigned)cdiv64(ldk, 32), (unsigned)cdiv64(N, 32)), 256, 0, st>>>(B, ldb, K, N, b_hi, b_lo, ldk, perm64);
     }
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;

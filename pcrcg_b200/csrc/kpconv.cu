@@ -710,8 +710,246 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
     if (blockIdx.y == 0 && lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
 }
 
-static int g_agg_simt = 0;
+// ---------------------------------------------------------------------------------------------
+// Persistent, software-pipelined form of the bf16x3 aggregation (H <= 64).  The one-point-per-warp kernel above spends a
+// third of its issue cycles waiting on L2 (long scoreboard: neighbour indices -> feature rows -> coordinates are three
+// dependent round trips per point, hidden only by the ~17 other resident warps).  Here a warp walks over many points and
+// keeps one 16-neighbour k-step in flight while it multiplies the previous one:
+//     iteration i:  cp.async of k-step i+1 (other buffer)  |  coordinates of k-step i+1 -> registers  |  wait k-step i
+//                   MMAs of k-step i  |  coordinates -> shared  |  (last k-step of a point: transposed store, which uses
+//                   the buffer just consumed as scratch)
+// The neighbour indices (and row flags) of the NEXT point are requested when the current point starts.  Shared memory
+// per warp is unchanged (2 buffers x 16 rows instead of 1 x 32), so residency stays at 5 CTAs / SM.
+constexpr int ABP_ROWS = 16;
+constexpr int ABP_BUF_BYTES = 2 * ABP_ROWS * AB_PITCH;                        // hi + lo rows of one k-step (= stmatrix scratch)
+constexpr int ABP_WARP_BYTES = 2 * ABP_BUF_BYTES + 2 * ABP_ROWS * 16;         // two buffers + two coordinate blocks
+constexpr int ABP_SMEM = AB_WARPS * ABP_WARP_BYTES;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo, int cin, int ldxs,
+    const uint8_t* __restrict__ rowflag, const float* __restrict__ kpts, int K, float inv_extent,
+    __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo, int ldk, float* __restrict__ inv_cnt)
+{
+    extern __shared__ __align__(16) uint8_t smem_b[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int stride = gridDim.x * AB_WARPS;
+    int n = blockIdx.x * AB_WARPS + w;
+    if (n >= nq) return;
+    uint8_t* s_buf = smem_b + (size_t)w * ABP_WARP_BYTES;                    // buffer b: hi rows at b*BUF, lo rows at b*BUF + 16*PITCH
+    float* s_xyz = reinterpret_cast<float*>(s_buf + 2 * ABP_BUF_BYTES);       // [2][16][4]
+    const uint32_t a_buf = (uint32_t)__cvta_generic_to_shared(s_buf);
+    const int g = lane >> 2, t = lane & 3;
+    const int c0 = blockIdx.y * 64;
+    const bool k1ok = g + 8 < K, k0ok = g < K;
+    const int ka = k0ok ? g : 0, kb = k1ok ? g + 8 : 0;
+    const float k0x = -2.f * kpts[3 * ka], k0y = -2.f * kpts[3 * ka + 1], k0z = -2.f * kpts[3 * ka + 2];
+    const float k1x = -2.f * kpts[3 * kb], k1y = -2.f * kpts[3 * kb + 1], k1z = -2.f * kpts[3 * kb + 2];
+    const float k0n = k0ok ? 0.25f * (k0x * k0x + k0y * k0y + k0z * k0z) : 1e30f;
+    const float k1n = k1ok ? 0.25f * (k1x * k1x + k1y * k1y + k1z * k1z) : 1e30f;
+    const int chunk = lane & 7, plane = (lane >> 3) & 1, rsel = lane >> 4;
+    const __nv_bfloat16* xp = (plane ? x_lo : x_hi) + c0 + chunk * 8;
+    const uint32_t dst_off = (uint32_t)(plane * ABP_ROWS * AB_PITCH + chunk * 16 + rsel * AB_PITCH);
+    const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
+
+    // neighbour indices of a point: the RAW values are requested early (load_raw) and only clamped to the shadow convention
+    // when the point is about to start (clamp_idx), so the load latency hides behind the previous point's k-steps
+    auto load_raw = [&](int p, IdxT& r0, IdxT& r1) {
+        const IdxT* row = idx + (size_t)min(p, nq - 1) * idx_stride;
+        r0 = row[lane < H ? lane : 0];
+        r1 = row[lane + 32 < H ? lane + 32 : 0];
+    };
+    auto clamp_idx = [&](int p, IdxT r0, IdxT r1, int& j0, int& j1) {
+        const long long v0 = (long long)r0, v1 = (long long)r1;
+        j0 = (p < nq && lane < H && v0 >= 0 && v0 < ns) ? (int)v0 : ns;
+        j1 = (p < nq && lane + 32 < H && v1 >= 0 && v1 < ns) ? (int)v1 : ns;
+    };
+    // k-steps (of 16 neighbours) that hold at least one real neighbour, as a 4-bit mask
+    auto step_mask = [&](int j0, int j1) -> uint32_t {
+        const uint32_t m0 = __ballot_sync(0xffffffffu, j0 < ns), m1 = __ballot_sync(0xffffffffu, j1 < ns);
+        return ((m0 & 0xffffu) ? 1u : 0u) | ((m0 >> 16) ? 2u : 0u) | ((m1 & 0xffffu) ? 4u : 0u) | ((m1 >> 16) ? 8u : 0u);
+    };
+    // stage k-step s of a point (neighbour registers j0 / j1) into buffer b: 8 cp.async per lane, 2 rows per instruction
+    auto stage = [&](int j0, int j1, int s, int b) {
+        const int jsrc = s < 2 ? j0 : j1;
+        const uint32_t dst = a_buf + (uint32_t)(b * ABP_BUF_BYTES) + dst_off;
+#pragma unroll
+        for (int r = 0; r < ABP_ROWS; r += 2) {
+            const int j = __shfl_sync(0xffffffffu, jsrc, ((s & 1) << 4) + r + rsel);
+            const bool v = j < ns;
+            const void* src = xp + (size_t)((unsigned)(v ? j : 0) * (unsigned)ldxs);
+            const int sz = v ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(r * AB_PITCH)), "l"(src), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // raw coordinates of the neighbour this lane (< 16) owns in k-step s
+    auto load_xyz = [&](int j0, int j1, int s, float& x, float& y, float& z) -> bool {
+        const int j = __shfl_sync(0xffffffffu, s < 2 ? j0 : j1, ((s & 1) << 4) + (lane & 15));
+        const bool v = j < ns;
+        if (v && lane < 16) { const float* sp = s_pts + 3 * (size_t)j; x = sp[0]; y = sp[1]; z = sp[2]; }
+        return v;
+    };
+
+    // write the coordinate block of a staged k-step: p' = p - q and |p'|^2 (1e30 for a shadow: influence exactly 0)
+    auto put_xyz = [&](int blk, bool v, float x, float y, float z, float ox, float oy, float oz) {
+        if (lane < 16) {
+            const float px = x - ox, py = y - oy, pz = z - oz;
+            *reinterpret_cast<float4*>(s_xyz + blk * (ABP_ROWS * 4) + lane * 4) =
+                v ? make_float4(px, py, pz, fmaf(px, px, fmaf(py, py, pz * pz))) : make_float4(0.f, 0.f, 0.f, 1e30f);
+        }
+    };
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+    // multiply the k-step held by buffer blk into acc
+    auto compute = [&](int blk) {
+        const float* xyz = s_xyz + blk * (ABP_ROWS * 4);
+        float wv[2][4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int rn = 2 * t + (e & 1) + (e >> 1) * 8;
+            const float4 p = *reinterpret_cast<const float4*>(xyz + rn * 4);
+            const float d0 = fabsf(fmaf(p.x, k0x, fmaf(p.y, k0y, fmaf(p.z, k0z, p.w + k0n))));
+            const float d1 = fabsf(fmaf(p.x, k1x, fmaf(p.y, k1y, fmaf(p.z, k1z, p.w + k1n))));
+            wv[0][e] = fmaxf(0.f, fmaf(-sqrt_approx(d0), inv_extent, 1.f));
+            wv[1][e] = fmaxf(0.f, fmaf(-sqrt_approx(d1), inv_extent, 1.f));
+        }
+        uint32_t ahi[4], alo[4];
+        ahi[0] = pack_split(wv[0][0], wv[0][1], alo[0]);
+        ahi[1] = pack_split(wv[1][0], wv[1][1], alo[1]);
+        ahi[2] = pack_split(wv[0][2], wv[0][3], alo[2]);
+        ahi[3] = pack_split(wv[1][2], wv[1][3], alo[3]);
+        const uint32_t base_hi = a_buf + (uint32_t)(blk * ABP_BUF_BYTES) + lm_off, base_lo = base_hi + ABP_ROWS * AB_PITCH;
+#pragma unroll
+        for (int np = 0; np < 4; np++) {
+            uint32_t bh[4], bl[4];
+            ldmatrix_x4_trans(bh, base_hi + np * 32);
+            ldmatrix_x4_trans(bl, base_lo + np * 32);
+            mma_bf16(acc[2 * np], alo, bh[0], bh[1]);
+            mma_bf16(acc[2 * np + 1], alo, bh[2], bh[3]);
+            mma_bf16(acc[2 * np], ahi, bl[0], bl[1]);
+            mma_bf16(acc[2 * np + 1], ahi, bl[2], bl[3]);
+            mma_bf16(acc[2 * np], ahi, bh[0], bh[1]);
+            mma_bf16(acc[2 * np + 1], ahi, bh[2], bh[3]);
+        }
+    };
+    // D [16 kp x 64 ch] of point pt -> bf16 hi / lo planes, straight from the accumulator registers: inside the slab the
+    // channels are stored in kperm64 order (common.cuh), which makes a thread's tiles 0-3 / 4-7 one 16-byte piece each and
+    // the four threads of a kernel-point row 64 contiguous bytes -- no shared-memory transposition.  acc is cleared.
+    auto store_point = [&](int pt) {
+        const size_t ebase = (size_t)pt * ldk + c0 + 8 * t;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const int kp = g + 8 * hh;
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) h[nt] = pack_split(acc[nt][2 * hh], acc[nt][2 * hh + 1], l[nt]);
+            if (kp < K) {
+                const size_t e = ebase + (size_t)kp * cin;
+                *reinterpret_cast<uint4*>(wf_hi + e) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(wf_hi + e + 32) = make_uint4(h[4], h[5], h[6], h[7]);
+                *reinterpret_cast<uint4*>(wf_lo + e) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(wf_lo + e + 32) = make_uint4(l[4], l[5], l[6], l[7]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    };
+
+    // ---- prologue: first point, its first k-step into buffer 0 --------------------------------------------------
+    int j0, j1;
+    {
+        IdxT r0, r1;
+        load_raw(n, r0, r1);
+        clamp_idx(n, r0, r1, j0, j1);
+    }
+    uint32_t smask = step_mask(j0, j1);
+    int s = smask ? __ffs(smask) - 1 : -1;
+    float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
+    int b = 0;
+    if (s >= 0) {
+        stage(j0, j1, s, 0);
+        float x = 0.f, y = 0.f, z = 0.f;
+        const bool v = load_xyz(j0, j1, s, x, y, z);
+        put_xyz(0, v, x, y, z, qx, qy, qz);
+    }
+
+    while (n < nq) {
+        // neighbour indices and query of the NEXT point, row flags of this one: requested now, used when this point ends
+        const int nn = n + stride;
+        IdxT nr0, nr1;
+        load_raw(nn, nr0, nr1);
+        int nj0 = ns, nj1 = ns;
+        const size_t qo = 3 * (size_t)min(nn, nq - 1);
+        const float nqx = q_pts[qo], nqy = q_pts[qo + 1], nqz = q_pts[qo + 2];
+        uint8_t f0 = 0, f1 = 0;                  // row flags of this point's neighbours (compared when the point ends)
+        if (blockIdx.y == 0) { f0 = rowflag[j0 < ns ? j0 : 0]; f1 = rowflag[j1 < ns ? j1 : 0]; }
+        uint32_t nmask = 0;
+        int ns_first = -1;                       // first real k-step of the next point, once known
+
+        if (s < 0) {
+            // a point without any real neighbour: zero rows; nothing of the next point is in flight yet
+            store_point(n);
+            clamp_idx(nn, nr0, nr1, nj0, nj1);
+            nmask = step_mask(nj0, nj1);
+            ns_first = (nn < nq && nmask) ? __ffs(nmask) - 1 : -1;
+            if (ns_first >= 0) {
+                stage(nj0, nj1, ns_first, b);
+                float x = 0.f, y = 0.f, z = 0.f;
+                const bool v = load_xyz(nj0, nj1, ns_first, x, y, z);
+                put_xyz(b, v, x, y, z, nqx, nqy, nqz);
+            }
+        } else {
+            while (true) {
+                // what follows (n, s): the next real k-step of this point, else the first one of the next point
+                const uint32_t rest = smask & ~((2u << s) - 1u);
+                const bool same = rest != 0u;
+                int s2;
+                if (same) s2 = __ffs(rest) - 1;
+                else {
+                    clamp_idx(nn, nr0, nr1, nj0, nj1);
+                    nmask = step_mask(nj0, nj1);
+                    ns_first = (nn < nq && nmask) ? __ffs(nmask) - 1 : -1;
+                    s2 = ns_first;
+                }
+                float x = 0.f, y = 0.f, z = 0.f;
+                bool v2 = false;
+                if (s2 >= 0) {
+                    stage(same ? j0 : nj0, same ? j1 : nj1, s2, b ^ 1);
+                    v2 = load_xyz(same ? j0 : nj0, same ? j1 : nj1, s2, x, y, z);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                compute(b);
+                if (s2 >= 0) put_xyz(b ^ 1, v2, x, y, z, same ? qx : nqx, same ? qy : nqy, same ? qz : nqz);
+                __syncwarp();
+                if (!same) break;
+                s = s2;
+                b ^= 1;
+            }
+            store_point(n);
+            b ^= 1;                              // the next point's first k-step is in flight in the other buffer
+        }
+        if (blockIdx.y == 0) {
+            const int cnt = __popc(__ballot_sync(0xffffffffu, j0 < ns && f0 != 0)) + __popc(__ballot_sync(0xffffffffu, j1 < ns && f1 != 0));
+            if (lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
+        }
+        n = nn;
+        j0 = nj0; j1 = nj1;
+        qx = nqx; qy = nqy; qz = nqz;
+        smask = nmask;
+        s = ns_first;
+    }
+}
+
+static int g_agg_simt = 0, g_agg_pipelined = 1;
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
+void kpconv_set_agg_pipelined(int v) { g_agg_pipelined = v; }
 
 template <typename IdxT, bool SPLIT>
 static int launch_agg(const float* q_pts, int nq, const float* s_pts, int ns, const IdxT* idx, int H, int idx_stride, const float* x,
@@ -766,6 +1004,7 @@ int gemm_tc_presplit_dev(const void* a_hi, const void* a_lo, int ldk, const floa
 int gemm_force_simt_get();
 
 int gemm_tc_split_b_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi, void* b_lo, cudaStream_t st);
+int gemm_tc_split_b_perm_dev(const float* B, int ldb, int b_is_nk, int N, int K, int ldk, void* b_hi, void* b_lo, int perm64, cudaStream_t st);
 int gemm_tc_core_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N, int K,
                      const float* row_scale, cudaStream_t st);
 int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int ldk, float* C, int ldc, int M, int N,
@@ -831,9 +1070,13 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
             PCRCG_CUDA(cudaGetLastError());
         }
     }
+    // which aggregation kernel runs (the same for every chunk): bf16 planes -> ldmatrix kernels; the pipelined one writes its
+    // 64-channel slabs in kperm64 order, so the weights are split with the matching K permutation
+    const bool planes = tc && x_hi != nullptr && x_lo != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 && !g_agg_simt && ns > 0;
+    const bool pipelined = planes && g_agg_pipelined && H <= 64;
     if (tc) {
         ProfScope prof(PC_GEMM, st, 0);
-        PCRCG_TRY(gemm_tc_split_b_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, st));
+        PCRCG_TRY(gemm_tc_split_b_perm_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, pipelined ? 1 : 0, st));
     }
     const size_t idx_bytes = idx_is_i64 ? 8 : 4;
     int it = 0;
@@ -847,8 +1090,21 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
         {
             ProfScope prof(PC_KPCONV_AGG, st, 1);
             int rc;
-            const bool planes = tc && x_hi != nullptr && x_lo != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 && !g_agg_simt && ns > 0;
-            if (planes) {
+            if (pipelined) {
+                // persistent: ~5 resident CTAs per SM in total, each warp walks over points with a fixed stride
+                const unsigned gy = (unsigned)(cin / 64);
+                unsigned gx = (unsigned)cdiv64(kNumSMs * 5, gy);
+                if ((int64_t)gx > cdiv64(rows, AB_WARPS)) gx = (unsigned)cdiv64(rows, AB_WARPS);
+                dim3 grid(gx, gy);
+                if (idx_is_i64)
+                    k_kpconv_aggregate_bf16p<long long><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                else
+                    k_kpconv_aggregate_bf16p<int><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                rc = cudaGetLastError() == cudaSuccess ? PCRCG_OK : PCRCG_ERR;
+                if (rc) set_error("kpconv: pipelined bf16 aggregate launch failed");
+            } else if (planes) {
                 dim3 grid((unsigned)cdiv64(rows, AB_WARPS), (unsigned)(cin / 64));
                 if (idx_is_i64)
                     k_kpconv_aggregate_bf16<long long><<<grid, AB_WARPS * 32, AB_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
