@@ -877,11 +877,13 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
         put_xyz(0, v, x, y, z, qx, qy, qz);
     }
 
+    IdxT nr0, nr1;                               // raw neighbour indices of the next point (requested one point earlier)
+    load_raw(n + stride, nr0, nr1);
     while (n < nq) {
-        // neighbour indices and query of the NEXT point, row flags of this one: requested now, used when this point ends
+        // requested now: neighbour indices of the point AFTER the next one, query of the next point, row flags of this one
         const int nn = n + stride;
-        IdxT nr0, nr1;
-        load_raw(nn, nr0, nr1);
+        IdxT fr0, fr1;
+        load_raw(nn + stride, fr0, fr1);
         int nj0 = ns, nj1 = ns;
         const size_t qo = 3 * (size_t)min(nn, nq - 1);
         const float nqx = q_pts[qo], nqy = q_pts[qo + 1], nqz = q_pts[qo + 2];
@@ -941,6 +943,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
         }
         n = nn;
         j0 = nj0; j1 = nj1;
+        nr0 = fr0; nr1 = fr1;
         qx = nqx; qy = nqy; qz = nqz;
         smask = nmask;
         s = ns_first;
