@@ -224,6 +224,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
+    # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import torch
     from pcrcg_b200 import blocks, pipeline

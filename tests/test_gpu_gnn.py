@@ -174,3 +174,17 @@ def test_point2node_and_node_visibility_vs_reference_golden():
     assert si.dtype == torch.int64 and np.array_equal(si.cpu().numpy(), g["src_idx"]) and np.array_equal(ti.cpu().numpy(), g["tgt_idx"])
     assert np.array_equal(sv.cpu().numpy(), g["src_node_vis"]) and np.array_equal(tv.cpu().numpy(), g["tgt_node_vis"])
     assert np.array_equal(dataloader.point2node(_d(g["src_nodes"]), _d(g["src_points"])).cpu().numpy(), g["src_idx"])
+
+
+def test_edge_cases_small_clouds_and_empty_inputs():
+    """a cloud with fewer than k+1 nodes repeats the query in its kNN list (the reference's topk would raise); empty inputs
+    are no-ops"""
+    pts = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 2, 0], [5, 5, 5], [5, 5, 6]], device=DEV)
+    idx = ops.knn(pts, ops.cloud_starts([3, 2]), 3).cpu().numpy()
+    assert idx[0].tolist() == [1, 2, 0] and idx[3].tolist() == [4, 3, 3] and idx[4].tolist() == [3, 4, 4]
+    empty = torch.zeros((0, 3), device=DEV)
+    assert ops.knn(empty, ops.cloud_starts([0]), 4).shape == (0, 4)
+    assert ops.l2_normalize(torch.zeros((0, 8), device=DEV)).shape == (0, 8)
+    assert ops.bias_act(torch.zeros((0, 8), device=DEV), torch.zeros(8, device=DEV), 0.0).shape == (0, 8)
+    z = ops.l2_normalize(torch.zeros((3, 8), device=DEV))              # F.normalize eps: zero rows stay zero
+    assert float(z.abs().max()) == 0.0
