@@ -513,6 +513,149 @@ __global__ void __launch_bounds__(256) k_kpconv_aggregate_small(
 }
 
 // ---------------------------------------------------------------------------------------------
+// First layer (cin <= 4, e.g. the all-ones feature of the reference pipeline, cin = 1): the WHOLE KPConv in one kernel.
+// 8 threads per query point (four points per warp, 32 per block).  (1) the point's neighbourhood is staged once in shared
+// memory by its 8 threads: one float4 (p - q, first feature) per neighbour (+ one with the other features when cin > 1);
+// (2) thread t accumulates kernel points t and t + 8 over the neighbours (one broadcast LDS.128 per neighbour and thread);
+// (3) the [K*cin] x cout weight contraction: the aggregates travel by shuffle inside the 8-thread group, thread t produces
+// the NJ = cout/8 consecutive output channels t*NJ.. from weights held in shared memory as [K*cin][8][NJ]; (4) x 1/neighbour
+// count, row-contiguous store.  Replaces aggregate_small + the fp32 CUDA-core contraction and their [Nq, K*cin] round trip.
+constexpr int SF_HMAX = 64;
+constexpr int SF_PTS = 32;                        // points per block
+
+template <typename IdxT, int CIN, int NJ>
+__global__ void __launch_bounds__(256) k_kpconv_small_fused(
+    const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
+    int idx_stride, const float* __restrict__ x, int ldx, const uint8_t* __restrict__ rowflag, const float* __restrict__ kpts, int K,
+    float inv_extent, const float* __restrict__ weights, float* __restrict__ out)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int REC = CIN > 1 ? 2 : 1;                                 // float4 records per neighbour
+    float4* s_nb = reinterpret_cast<float4*>(smem_f);                    // [SF_PTS][SF_HMAX][REC]
+    float* s_w = smem_f + SF_PTS * SF_HMAX * REC * 4;                    // [K*CIN][NJ/4][8][4]  (see the staging loop)
+    constexpr int COUT = 8 * NJ;
+    const int t = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int n = blockIdx.x * SF_PTS + pl;
+    for (int e = threadIdx.x; e < K * CIN * COUT; e += 256) {
+        const int kc = e / COUT, c = e - kc * COUT;                      // weights [K][CIN][COUT] row-major; channel c = t*NJ + j
+        const int tt = c / NJ, j = c % NJ;
+        // [kc][j / 4][t][4] when NJ % 4 == 0: the 8 threads of a point read 8 adjacent float4 (bank-conflict free); else [kc][t][NJ]
+        s_w[NJ % 4 == 0 ? ((kc * (NJ / 4) + j / 4) * 8 + tt) * 4 + (j & 3) : (kc * 8 + tt) * NJ + j] = weights[e];
+    }
+    const bool live = n < nq;
+    const int nn = live ? n : nq - 1;
+    const float qx = q_pts[3 * (size_t)nn], qy = q_pts[3 * (size_t)nn + 1], qz = q_pts[3 * (size_t)nn + 2];
+    float4* nb = s_nb + pl * (SF_HMAX * REC);
+    int cnt = 0;
+    const IdxT* row = idx + (size_t)nn * idx_stride;
+    for (int h = t; h < H; h += 8) {
+        const long long j = (long long)row[h];
+        float4 a = make_float4(1e15f, 1e15f, 1e15f, 0.f), f = make_float4(0.f, 0.f, 0.f, 0.f);    // shadow: influence 0, zero features
+        if (j >= 0 && j < ns) {
+            const float* sp = s_pts + 3 * (size_t)j;
+            const float* xr = x + (size_t)j * ldx;
+            a = make_float4(sp[0] - qx, sp[1] - qy, sp[2] - qz, xr[0]);
+            if (CIN > 1) f.x = xr[1];
+            if (CIN > 2) f.y = xr[2];
+            if (CIN > 3) f.z = xr[3];
+            cnt += rowflag[j];
+        }
+        nb[REC * h] = a;
+        if (CIN > 1) nb[REC * h + 1] = f;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o, 8);
+    __syncthreads();                                                     // weights + every point's neighbourhood staged
+
+    // (2) aggregates of kernel points t and t + 8 (a missing kernel point sits far away: influence exactly 0)
+    const bool ok0 = t < K, ok1 = t + 8 < K;
+    const float k0x = ok0 ? kpts[3 * t] : 1e15f, k0y = ok0 ? kpts[3 * t + 1] : 1e15f, k0z = ok0 ? kpts[3 * t + 2] : 1e15f;
+    const float k1x = ok1 ? kpts[3 * (t + 8)] : 1e15f, k1y = ok1 ? kpts[3 * (t + 8) + 1] : 1e15f, k1z = ok1 ? kpts[3 * (t + 8) + 2] : 1e15f;
+    float acc[2][CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; c++) acc[0][c] = acc[1][c] = 0.f;
+#pragma unroll 4
+    for (int h = 0; h < H; h++) {
+        const float4 a = nb[REC * h];
+        float f[4] = { a.w, 0.f, 0.f, 0.f };
+        if (CIN > 1) { const float4 g = nb[REC * h + 1]; f[1] = g.x; f[2] = g.y; f[3] = g.z; }
+        float dx = a.x - k0x, dy = a.y - k0y, dz = a.z - k0z;
+        float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
+        const float w0 = fmaxf(0.f, fmaf(-d2 * rsqrtf(d2), inv_extent, 1.f));
+        dx = a.x - k1x; dy = a.y - k1y; dz = a.z - k1z;
+        d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
+        const float w1 = fmaxf(0.f, fmaf(-d2 * rsqrtf(d2), inv_extent, 1.f));
+#pragma unroll
+        for (int c = 0; c < CIN; c++) { acc[0][c] = fmaf(w0, f[c], acc[0][c]); acc[1][c] = fmaf(w1, f[c], acc[1][c]); }
+    }
+    // (3) contraction: out[c] = sum_{kp,ci} wf[kp][ci] * W[kp][ci][c] for this thread's NJ channels
+    float o[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) o[j] = 0.f;
+    for (int kp = 0; kp < K; kp++) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ci++) {
+            const float lo = __shfl_sync(0xffffffffu, acc[0][ci], kp & 7, 8), hi = __shfl_sync(0xffffffffu, acc[1][ci], kp & 7, 8);
+            const float v = kp < 8 ? lo : hi;
+            const float* wr = s_w + ((kp * CIN + ci) * 8 + t) * NJ;
+            if (NJ % 4 == 0) {
+                const float4* w4p = reinterpret_cast<const float4*>(s_w) + (kp * CIN + ci) * (NJ / 4) * 8 + t;
+#pragma unroll
+                for (int j = 0; j + 3 < NJ; j += 4) {
+                    const float4 w4 = w4p[(j / 4) * 8];
+                    o[j] = fmaf(v, w4.x, o[j]); o[j + 1] = fmaf(v, w4.y, o[j + 1]);
+                    o[j + 2] = fmaf(v, w4.z, o[j + 2]); o[j + 3] = fmaf(v, w4.w, o[j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; j++) o[j] = fmaf(v, wr[j], o[j]);
+            }
+        }
+    }
+    if (live) {
+        const float sc = 1.0f / (float)(cnt > 1 ? cnt : 1);                // models/blocks.py:369-372
+        float* dst = out + (size_t)n * COUT + t * NJ;
+        if (NJ % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j + 3 < NJ; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * sc, o[j + 1] * sc, o[j + 2] * sc, o[j + 3] * sc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NJ; j++) dst[j] = o[j] * sc;
+        }
+    }
+}
+
+template <typename IdxT>
+static bool launch_small_fused(const float* q_pts, int nq, const float* s_pts, int ns, const IdxT* idx, int H, int idx_stride, const float* x,
+                               int cin, const uint8_t* rowflag, const float* kpts, int K, float inv_extent, const float* weights, int cout,
+                               float* out, cudaStream_t st)
+{
+    if (cin > 4 || H > SF_HMAX || (cout != 16 && cout != 32 && cout != 64 && cout != 128 && cout != 256)) return false;
+    const size_t smem = (size_t)SF_PTS * SF_HMAX * (cin > 1 ? 2 : 1) * 16 + (size_t)K * cin * cout * sizeof(float);
+    if (smem > 160 * 1024) return false;
+    const unsigned grid = (unsigned)cdiv64(nq, SF_PTS);
+#define PCRCG_SF(C_, NJ_)                                                                                                              \
+    do {                                                                                                                               \
+        cudaFuncSetAttribute(k_kpconv_small_fused<IdxT, C_, NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        k_kpconv_small_fused<IdxT, C_, NJ_><<<grid, 256, smem, st>>>(q_pts, nq, s_pts, ns, idx, H, idx_stride, x, cin, rowflag, kpts, K, \
+                                                                     inv_extent, weights, out);                                       \
+    } while (0)
+#define PCRCG_SF_C(C_)                                                                                            \
+    do {                                                                                                          \
+        if (cout == 16) PCRCG_SF(C_, 2); else if (cout == 32) PCRCG_SF(C_, 4); else if (cout == 64) PCRCG_SF(C_, 8); \
+        else if (cout == 128) PCRCG_SF(C_, 16); else PCRCG_SF(C_, 32);                                             \
+    } while (0)
+    if (cin == 1) PCRCG_SF_C(1);
+    else if (cin == 2) PCRCG_SF_C(2);
+    else if (cin == 3) PCRCG_SF_C(3);
+    else PCRCG_SF_C(4);
+#undef PCRCG_SF_C
+#undef PCRCG_SF
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // bf16x3 variant of the 64-channel-slab tensor-core aggregation, used when the producer of the features
 // already emitted them as bf16 (hi, lo) planes (instance norm epilogue, dense.cu).  Compared with the
 // 3xTF32 kernel above: mma.sync m16n8k16 (16 neighbours per step: half the MMAs), B fragments come
@@ -950,7 +1093,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
     }
 }
 
-static int g_agg_simt = 0, g_agg_pipelined = 1;
+// first_layer_fused: measured on B200 at 1.33 ms per 32-pair step against 0.88 + 0.31 ms for aggregate_small + the CUDA-core
+// contraction (one short-lived block per 32 points: latency-bound behind its staging barrier) -> opt-in until it is persistent
+static int g_agg_simt = 0, g_agg_pipelined = 1, g_small_fused = 0;
+void kpconv_set_small_fused(int v) { g_small_fused = v; }
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
 void kpconv_set_agg_pipelined(int v) { g_agg_pipelined = v; }
 
@@ -1082,6 +1228,17 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
         PCRCG_TRY(gemm_tc_split_b_perm_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, pipelined ? 1 : 0, st));
     }
     const size_t idx_bytes = idx_is_i64 ? 8 : 4;
+    if (cin <= 4 && !g_agg_simt && !gemm_force_simt_get() && stats_acc == nullptr && ns > 0 && g_small_fused) {
+        // first layer: aggregation + contraction + 1/count in one kernel
+        ProfScope prof(PC_KPCONV_AGG, st, 1);
+        const bool done = idx_is_i64
+            ? launch_small_fused<long long>(q_pts, (int)nq, s_pts, (int)ns, (const long long*)idx, H, idx_stride, x, cin, rowflag, kpts, K, inv_extent, weights, cout, out, st)
+            : launch_small_fused<int>(q_pts, (int)nq, s_pts, (int)ns, (const int*)idx, H, idx_stride, x, cin, rowflag, kpts, K, inv_extent, weights, cout, out, st);
+        if (done) {
+            PCRCG_CUDA(cudaGetLastError());
+            return PCRCG_OK;
+        }
+    }
     int it = 0;
     for (int64_t r0 = 0; r0 < nq; r0 += chunk, it++) {
         const int rows = (int)((nq - r0) < chunk ? (nq - r0) : chunk);

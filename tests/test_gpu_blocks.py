@@ -233,3 +233,28 @@ def test_kpconv_shadow_steps_anywhere_and_epilogue_statistics():
             var = (blk_ * blk_).mean(0) - mu * mu
             assert float((mean[k].double() - mu).abs().max()) < 1e-6 + 1e-5 * float(mu.abs().max())
             assert float(((rstd[k].double() - 1 / torch.sqrt(var + 1e-5)).abs() * torch.sqrt(var + 1e-5)).max()) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,H", [(1, 128, 34), (1, 32, 30), (3, 64, 40), (4, 256, 64), (2, 16, 7), (1, 64, 70), (1, 48, 20)])
+def test_first_layer_fused_kpconv_vs_port(cin, cout, H, contraction_path):
+    """cin <= 4 (the reference's first layer has the all-ones feature, cin = 1): aggregation + contraction in one kernel
+    (H <= 64, cout in {16..256}); the other shapes of the sweep take the two-kernel path.  Mixed-sign features exercise the
+    neighbour-count rule (models/blocks.py:369-372)."""
+    src, tgt, _ = synthetic.match3d_pair(5, n_target=1000)
+    pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+    rows = ops.batch_query(_d(pts), _d(pts), _d(lens), _d(lens), 0.0625 if H < 60 else 0.1, H)
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(len(pts), cin, generator=g) if cin > 1 else torch.ones(len(pts), 1)
+    w = torch.randn(15, cin, cout, generator=g) / np.sqrt(15 * cin)
+    kp = torch.randn(15, 3, generator=g) * 0.03
+    ref = bp.kpconv(torch.from_numpy(pts), torch.from_numpy(pts), rows.cpu(), x, kp, w, 0.05)
+    from pcrcg_b200._lib import lib
+    for fused in (1, 0):                                    # opt-in one-kernel path, then the default two-kernel path
+        assert lib().pcrcg_set_option(b"first_layer_fused", fused) == 0
+        try:
+            out = ops.kpconv_forward(_d(pts), _d(pts), rows, x.to(DEV), kp.to(DEV), w.to(DEV), 0.05)
+            assert _err(out, ref) < 1e-4, fused
+            out64 = ops.kpconv_forward(_d(pts), _d(pts), rows.long(), x.to(DEV), kp.to(DEV), w.to(DEV), 0.05)
+            assert torch.equal(out, out64)
+        finally:
+            lib().pcrcg_set_option(b"first_layer_fused", 0)
