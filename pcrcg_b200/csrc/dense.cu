@@ -210,19 +210,22 @@ __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, i
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= nq) return;
     const IdxT* row = idx + (size_t)n * idx_stride;
-    if ((C & 3) == 0 && H <= 64) {
-        int j0 = ns, j1 = ns;
-        if (lane < H) { long long v = (long long)row[lane]; j0 = (v >= 0 && v < ns) ? (int)v : ns; }
-        if (lane + 32 < H) { long long v = (long long)row[lane + 32]; j1 = (v >= 0 && v < ns) ? (int)v : ns; }
-        for (int cb = 0; cb < C; cb += 128) {               // warp-uniform trip count (shuffles inside)
+    if ((C & 3) == 0) {
+        for (int cb = 0; cb < C; cb += 128) {               // warp-uniform trip counts (shuffles inside)
             const int c = cb + 4 * lane;
             const bool act = c < C;
             float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            for (int h = 0; h < H; h++) {
-                const int j = __shfl_sync(0xffffffffu, h < 32 ? j0 : j1, h & 31);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act && j < ns) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)j * ldx + c));
-                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            for (int h0 = 0; h0 < H; h0 += 32) {            // 32 indices per round: one coalesced load, broadcast by shuffle
+                int jl = ns;
+                if (h0 + lane < H) { long long v = (long long)row[h0 + lane]; jl = (v >= 0 && v < ns) ? (int)v : ns; }
+                const int hn = min(32, H - h0);
+#pragma unroll 4
+                for (int h = 0; h < hn; h++) {
+                    const int j = __shfl_sync(0xffffffffu, jl, h);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act && j < ns) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)j * ldx + c));
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
             }
             if (H == 0) m = make_float4(0.f, 0.f, 0.f, 0.f);
             if (act) *reinterpret_cast<float4*>(out + (size_t)n * C + c) = m;

@@ -258,3 +258,17 @@ def test_first_layer_fused_kpconv_vs_port(cin, cout, H, contraction_path):
             assert torch.equal(out, out64)
         finally:
             lib().pcrcg_set_option(b"first_layer_fused", 0)
+
+
+@pytest.mark.parametrize("C,H", [(256, 102), (20, 70), (64, 33), (1024, 5), (4, 1)])
+def test_max_pool_long_lists_exact(C, H):
+    """KITTI-shaped limits are ~100 neighbours: the vectorised gather handles any list length; exact vs torch"""
+    g = torch.Generator().manual_seed(C + H)
+    ns, nq = 3000, 777
+    x = torch.randn(ns, C, generator=g)
+    idx = torch.randint(0, ns + 1, (nq, H), generator=g).to(torch.int32)       # ns = shadow
+    idx[::7, H // 2:] = ns
+    ref = torch.cat([x, torch.zeros(1, C)])[idx.long()].max(1)[0]
+    out = ops.max_pool(x.to(DEV), idx.to(DEV))
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(ops.max_pool(x.to(DEV), idx.long().to(DEV)).cpu(), ref)
