@@ -79,3 +79,34 @@ def test_stacked_demo_pairs_roundtrip(demo_pair):
         shadow = nb >= 6 * n
         rel = torch.where(shadow, torch.full_like(nb, -1), nb - off)
         assert torch.equal(rel[0].expand_as(rel), rel)
+
+
+def test_kpconv_support_permutation_invariance_full_size(demo_batch):
+    """Size-independent property at full size (39 939 query points x 38 neighbours, 64 -> 64 channels): relabelling the
+    support rows (features, coordinates and the index lists remapped consistently) must not change ANY output bit -- the
+    neighbour order inside each list, hence every summation order, is unchanged; only the gather addresses move.  Run on both
+    aggregation kernels (pipelined bf16 planes, and the fp32-input tensor-core kernel)."""
+    from pcrcg_b200 import ops
+    _, cfg, b = demo_batch
+    pts, idx = b["points"][0], b["neighbors"][0]
+    n = pts.shape[0]
+    g = torch.Generator().manual_seed(11)
+    raw = torch.randn(n, 64, generator=g).to(DEV)
+    w = (torch.randn(15, 64, 64, generator=g) / 31.0).to(DEV)
+    kp = (torch.randn(15, 3, generator=g) * 0.03).to(DEV)
+    perm = torch.randperm(n, generator=g).to(DEV)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device=DEV)
+    inv_pad = torch.cat([inv, torch.tensor([n], device=DEV)])                    # the shadow index stays the shadow index
+    idx_p = inv_pad[idx.long()].to(torch.int32)
+    for planes in (True, False):
+        x = ops.instance_norm_act(raw, None, 0.1, emit_split=planes, emit_rowpos=planes)
+        xp = x[perm].contiguous()                       # the SAME feature values, rows relabelled (planes and row flags too)
+        if planes:
+            hi, lo, ld = x._pcrcg_split
+            xp._pcrcg_split = (hi[perm].contiguous(), lo[perm].contiguous(), ld)
+            xp._pcrcg_rowpos = x._pcrcg_rowpos[perm].contiguous()
+        out = ops.kpconv_forward(pts, pts, idx, x, kp, w, 0.05)
+        out_p = ops.kpconv_forward(pts, pts[perm], idx_p, xp, kp, w, 0.05)
+        assert torch.equal(out, out_p), f"planes={planes}"
+    assert float(out.abs().max()) > 0
