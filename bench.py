@@ -313,7 +313,6 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    L.pcrcg_profile_enable(1)
     launches0 = L.pcrcg_launch_count()
     barrier()
     t_begin = time.perf_counter()
@@ -326,6 +325,14 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = int(L.pcrcg_launch_count() - launches0)
+    # per-class device time: the same K steps once more with the library's event pairs around every kernel class (kept out of
+    # the region that defines `value`: ~300 extra event records per step are host work the product path does not do)
+    L.pcrcg_profile_enable(1)
+    barrier()
+    for _ in range(K):
+        flush.fill_(0.0)
+        path.run_device(pts_dev, lens_dev)
+    barrier()
     ncls = L.pcrcg_profile_classes()
     ms_arr, cnt_arr = (C.c_double * ncls)(), (C.c_int64 * ncls)()
     L.pcrcg_profile_report(ms_arr, cnt_arr)
