@@ -406,7 +406,7 @@ def main():
                 "config": {"workload": wl_name, "pairs_per_step_per_gpu": P, "points_per_level": Nlev, "limits": list(limits),
                            "first_feats_dim": cfg.first_feats_dim, "l2": "256 MiB flush write between timed iterations",
                            "contraction": "fp32 CUDA cores" if args.simt else
-                           "fp32 operands split into bf16 hi/lo: tcgen05 bf16x3 contraction + mma.sync bf16x3/3xTF32 aggregation, fp32 accumulate "
+                           "fp32 operands split into bf16 hi/lo: tcgen05 bf16x3 contraction + mma.sync bf16x3 aggregation, fp32 accumulate "
                            "(fp32 CUDA cores for ragged shapes such as Cin=1)",
                            "parallelism": f"pairs sharded by rank x{world}, no collective on the path"},
                 "clocks": clocks,

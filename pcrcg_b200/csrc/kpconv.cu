@@ -5,11 +5,17 @@
 //   wf[n,k,:] = sum_h w[n,k,h] * x[idx[n,h],:]
 //   out[n,:]  = (sum_k wf[n,k,:] @ W[k]) / max(1, #{h : sum_c x[idx[n,h],c] > 0})
 //
-// Stage 1 (this file, k_kpconv_aggregate): one warp per query point, lanes over channels.  For each
-// neighbour the 15 influence weights are computed once by lanes 0..14, published through shared
-// memory and applied to the coalesced feature row; the [K*Cin] aggregate stays in registers and is
-// written once.  Stage 2 is the [Nq, K*Cin] x [K*Cin, Cout] contraction (gemm.cu) with the
-// 1/count row scale in its epilogue.
+// Two stages: the AGGREGATION wf (this file) and the [Nq, K*Cin] x [K*Cin, Cout] CONTRACTION (gemm_tc.cu / gemm.cu) with the
+// 1/count row scale -- and optionally the InstanceNorm statistics of the result -- in its epilogue.  Aggregation kernels, in
+// dispatch order (kpconv_forward_dev / launch_agg):
+//   k_kpconv_aggregate_bf16p   features given as bf16 (hi, lo) planes, cin % 64 == 0, H <= 64: persistent, software-pipelined,
+//                              ldmatrix + mma.sync m16n8k16 bf16x3, register stores in kperm64 slab order   (every production layer)
+//   k_kpconv_aggregate_bf16    same inputs, any H: one point per warp, 32-row staging, stmatrix transposed stores
+//   k_kpconv_aggregate_small   cin <= 4 (first layer): one thread per (point, kernel point)
+//   k_kpconv_small_fused       cin <= 4, whole KPConv in one kernel (opt-in, see g_small_fused)
+//   k_kpconv_aggregate_mma64   fp32 features, cin % 64 == 0: cp.async staging + mma.sync m16n8k8 3xTF32
+//   k_kpconv_aggregate_mma     fp32 features, cin % 8 == 0: direct gathers + 3xTF32
+//   k_kpconv_aggregate         CUDA-core fallback for ragged cin (129: colour path) and the "aggregate_simt" parity anchor
 #include "common.cuh"
 
 #include <cuda_bf16.h>
