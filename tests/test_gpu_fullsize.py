@@ -110,3 +110,38 @@ def test_kpconv_support_permutation_invariance_full_size(demo_batch):
         out_p = ops.kpconv_forward(pts, pts[perm], idx_p, xp, kp, w, 0.05)
         assert torch.equal(out, out_p), f"planes={planes}"
     assert float(out.abs().max()) > 0
+
+
+def test_demo_pair_whole_network_vs_cpu_ports(demo_batch):
+    """config 1 at full size through the WHOLE descriptor network (indoor.yaml dims: encoder 256 -> 2048, GNN 512, 4 heads,
+    k = 10, decoder -> 32 + 2): final descriptors and scores vs the PyTorch-fp32 CPU restatements (oracle/blocks_port.py,
+    oracle/gcn_port.py; each pinned to the reference's own outputs) with the same weights and the same index lists."""
+    from oracle import gcn_port as gp
+    from pcrcg_b200 import architectures
+    pre, cfg, b = demo_batch
+    torch.manual_seed(5)
+    net = architectures.KPFCNN(cfg)
+    for m in net.encoder_blocks.modules():
+        if isinstance(m, blocks.KPConv):
+            m.set_kernel_points(torch.randn(15, 3) * 0.4 * m.radius)
+    with torch.no_grad():
+        net.epsilon.fill_(-2.0)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.to(DEV)
+    n0 = b["points"][0].shape[0]
+    fb = dict(b)
+    fb["features"] = torch.ones(n0, 1, device=DEV)
+    res = {k: v.cpu() for k, v in net(fb).items()}
+    assert res["feats_f"].shape == (n0, 32)
+    # CPU ports, stage by stage
+    cpu_batch = {k: [t.cpu().contiguous() for t in b[k]] for k in ("points", "neighbors", "pools", "upsamples")}
+    desc = bp.encoder_blocks_from_state_dict(sd, prefix="encoder_blocks.")
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        x, outs = bp.encoder(torch.ones(n0, 1), cpu_batch, desc)
+        xb = gp.bottleneck(x, cpu_batch["points"][3], b["stack_lengths"][3].cpu().numpy(), sd, cfg.nets, cfg.num_head, cfg.dgcnn_k)
+        Ws = [sd["decoder_blocks.1.mlp.weight"], sd["decoder_blocks.3.mlp.weight"], sd["decoder_blocks.5.mlp.weight"]]
+        feats, so, ss, _ = bp.decoder(xb, [outs[1], outs[4], outs[7]], cpu_batch, Ws, 32)
+    err = lambda a, r: float((a - r).abs().max() / r.abs().max().clamp_min(1e-30))
+    assert err(res["feats_f"], feats) < 1e-3, err(res["feats_f"], feats)
+    assert err(res["scores_overlap"], so) < 1e-3 and err(res["scores_saliency"], ss) < 1e-3
