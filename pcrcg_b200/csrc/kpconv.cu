@@ -1169,7 +1169,7 @@ int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi,
 // alternating buffers of at most WF_CHUNK_BYTES each, which bounds the workspace for very large
 // batches.  (Measured on B200: L2-sized 40 MB chunks -- meant to keep the intermediate out of HBM --
 // LOSE 25 %: a chunk is then < 148 contraction tiles and both kernels run under-filled; see DESIGN.md.)
-constexpr size_t WF_CHUNK_BYTES = 4ull << 30;
+constexpr size_t WF_CHUNK_BYTES = 8ull << 30;      // (one chunk up to 2.2 M query points at cin = 64: no split at 32 stacked pairs)
 
 static int64_t kpconv_chunk_rows(int64_t nq, size_t ldk)
 {
@@ -1183,7 +1183,8 @@ size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
 {
     size_t ldk = ((size_t)K * cin + 7) / 8 * 8;
     size_t chunk = (size_t)kpconv_chunk_rows(nq, ldk);
-    return 2 * align_up(chunk * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) +
+    const size_t nbuf = (int64_t)chunk < nq ? 2 : 1;          // the second (alternating) buffer only exists when the rows are chunked
+    return nbuf * align_up(chunk * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) +
            align_up((size_t)2048 * ldk * sizeof(float), 256) + 2048;      // + split weights for cout <= 2048
 }
 
@@ -1210,7 +1211,9 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     const int ldk = (KC + 7) / 8 * 8;
     const int64_t chunk = kpconv_chunk_rows(nq, (size_t)ldk);
     Workspace W(ws, ws_bytes);
-    float* wf_buf[2] = { W.take<float>((size_t)chunk * ldk), W.take<float>((size_t)chunk * ldk) };
+    float* wf_buf[2];
+    wf_buf[0] = W.take<float>((size_t)chunk * ldk);
+    wf_buf[1] = chunk < nq ? W.take<float>((size_t)chunk * ldk) : wf_buf[0];
     float* inv_cnt = W.take<float>((size_t)nq);
     uint8_t* rowflag_ws = W.take<uint8_t>((size_t)(ns > 0 ? ns : 1));
     const uint8_t* rowflag = rowflag_in != nullptr ? rowflag_in : rowflag_ws;
