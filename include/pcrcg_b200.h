@@ -127,6 +127,7 @@ int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* 
 void pcrcg_gemm_force_simt(int32_t on);
 /* A/B switches for measurements: "contraction_simt", "aggregate_simt" (CUDA-core variants of the two KPConv stages),
  * "aggregate_pipelined" (persistent software-pipelined bf16 aggregation, default 1; 0 = one point per warp),
+ * "kpconv_chunk_mb" (bound of one KPConv intermediate buffer in MiB, 0 = default 8192; query rows beyond it are processed in chunks),
  * "first_layer_fused" (cin <= 4: aggregation + contraction in one kernel; default 0, the two-kernel path measures faster),
  * "norm_vectorised" (float4 InstanceNorm apply kernel, default 1), "norm_variant" (0 = per-mode launch shape, 1..4 fixed),
  * "stats_debug" (contraction-epilogue statistics: 1 = no atomics, 2 = no column sums; timing ablation only). */

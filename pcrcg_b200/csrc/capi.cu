@@ -68,6 +68,7 @@ void dense_set_norm_variant(int);
 void kpconv_set_agg_simt(int);
 void kpconv_set_agg_pipelined(int);
 void kpconv_set_small_fused(int);
+void kpconv_set_chunk_mb(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
@@ -271,6 +272,7 @@ int pcrcg_set_option(const char* name, int32_t value)
     else if (!strcmp(name, "aggregate_simt")) kpconv_set_agg_simt(value);
     else if (!strcmp(name, "aggregate_pipelined")) kpconv_set_agg_pipelined(value);
     else if (!strcmp(name, "first_layer_fused")) kpconv_set_small_fused(value);
+    else if (!strcmp(name, "kpconv_chunk_mb")) kpconv_set_chunk_mb(value);
     else if (!strcmp(name, "stats_debug")) gemm_set_stats_dbg(value);
     else if (!strcmp(name, "norm_variant")) dense_set_norm_variant(value);
     else if (!strcmp(name, "norm_vectorised")) dense_set_norm_v4(value);

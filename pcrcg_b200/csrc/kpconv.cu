@@ -1169,7 +1169,9 @@ int gemm_tc_core_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi,
 // alternating buffers of at most WF_CHUNK_BYTES each, which bounds the workspace for very large
 // batches.  (Measured on B200: L2-sized 40 MB chunks -- meant to keep the intermediate out of HBM --
 // LOSE 25 %: a chunk is then < 148 contraction tiles and both kernels run under-filled; see DESIGN.md.)
-constexpr size_t WF_CHUNK_BYTES = 8ull << 30;      // (one chunk up to 2.2 M query points at cin = 64: no split at 32 stacked pairs)
+static size_t WF_CHUNK_BYTES = 8ull << 30;      // (one chunk up to 2.2 M query points at cin = 64: no split at 32 stacked pairs)
+
+void kpconv_set_chunk_mb(int mb) { WF_CHUNK_BYTES = mb > 0 ? (size_t)mb << 20 : 8ull << 30; }      // tests: force the chunked path
 
 static int64_t kpconv_chunk_rows(int64_t nq, size_t ldk)
 {

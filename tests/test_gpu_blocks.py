@@ -272,3 +272,27 @@ def test_max_pool_long_lists_exact(C, H):
     out = ops.max_pool(x.to(DEV), idx.to(DEV))
     assert torch.equal(out.cpu(), ref)
     assert torch.equal(ops.max_pool(x.to(DEV), idx.long().to(DEV)).cpu(), ref)
+
+
+def test_kpconv_chunked_intermediate_equals_unchunked():
+    """query rows beyond the intermediate-buffer bound are processed in chunks (alternating buffers, statistics sink with a
+    row offset): same bits as the single-chunk run, and the epilogue statistics still cover every row"""
+    from pcrcg_b200._lib import lib
+    src, tgt, _ = synthetic.match3d_pair(2, n_target=2600)
+    pts = np.concatenate([src, tgt]); lens = np.array([len(src), len(tgt)], np.int32)
+    rows = ops.batch_query(_d(pts), _d(pts), _d(lens), _d(lens), 0.0625, 34)
+    g = torch.Generator().manual_seed(8)
+    x = ops.instance_norm_act(torch.randn(len(pts), 64, generator=g).to(DEV), None, 0.1, emit_split=True, emit_rowpos=True)
+    w = (torch.randn(15, 64, 64, generator=g) / 31.0).to(DEV)
+    kp = (torch.randn(15, 3, generator=g) * 0.03).to(DEV)
+    seg = torch.tensor([0, 1500, len(pts)], dtype=torch.int32, device=DEV)
+    one = ops.kpconv_forward(_d(pts), _d(pts), rows, x, kp, w, 0.05, stat_segments=seg)
+    assert lib().pcrcg_set_option(b"kpconv_chunk_mb", 1) == 0          # 1 MiB -> 1024-row chunks (the minimum)
+    try:
+        many = ops.kpconv_forward(_d(pts), _d(pts), rows, x, kp, w, 0.05, stat_segments=seg)
+    finally:
+        lib().pcrcg_set_option(b"kpconv_chunk_mb", 0)
+    assert len(pts) > 3 * 1024 and torch.equal(one, many)
+    if hasattr(one, "_pcrcg_stats"):
+        assert torch.allclose(one._pcrcg_stats[0], many._pcrcg_stats[0], rtol=0, atol=1e-6)
+        assert torch.allclose(one._pcrcg_stats[1], many._pcrcg_stats[1], rtol=1e-5, atol=0)
