@@ -119,6 +119,62 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 // monotone float <-> int maps for atomicMin/atomicMax on floats
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// Per-cloud bounding boxes (ordered-int encoding, bbox[c] = {min x,y,z, max x,y,z}) of stacked clouds, one point per thread,
+// 256-thread blocks.  A warp that lies inside one cloud reduces by shuffle; a block that lies inside one cloud reduces its
+// 8 warps through shared memory and issues 6 atomics (instead of 48): the boxes of a stacked batch are a few hundred
+// addresses, so the atomics, not the 12 bytes per point, were the cost of this pass.
+__device__ __forceinline__ void bbox_accumulate(const float* __restrict__ pts, int n, const int32_t* __restrict__ starts, int nb,
+                                                int* __restrict__ bbox)
+{
+    __shared__ float s_red[8][6];
+    __shared__ int s_cloud[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool ok = i < n;
+    const int c = ok ? cloud_of(starts, nb, i) : -1;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (ok) { x = pts[3 * (size_t)i]; y = pts[3 * (size_t)i + 1]; z = pts[3 * (size_t)i + 2]; }
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool uniform = __all_sync(0xffffffffu, c == c0);
+    float mnx = x, mny = y, mnz = z, mxx = x, mxy = y, mxz = z;
+    if (uniform) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+        }
+    } else if (ok) {                       // a warp that straddles a cloud boundary: per-point atomics (rare)
+        int* b = bbox + 6 * c;
+        atomicMin(b + 0, f2ord(x)); atomicMin(b + 1, f2ord(y)); atomicMin(b + 2, f2ord(z));
+        atomicMax(b + 3, f2ord(x)); atomicMax(b + 4, f2ord(y)); atomicMax(b + 5, f2ord(z));
+    }
+    if (lane == 0) {
+        s_cloud[w] = uniform ? c0 : -2;    // -1: warp past the end, -2: handled above
+        s_red[w][0] = mnx; s_red[w][1] = mny; s_red[w][2] = mnz; s_red[w][3] = mxx; s_red[w][4] = mxy; s_red[w][5] = mxz;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        const int cw = lane < nw ? s_cloud[lane] : -1;
+        const int cb = __shfl_sync(0xffffffffu, cw, 0);
+        // every live warp of the block in the same cloud -> one set of atomics for the block; otherwise one per warp
+        const bool block_uniform = cb >= 0 && __all_sync(0xffffffffu, cw == cb || cw == -1);
+        if (block_uniform) {
+            if (lane < 6) {
+                float v = s_red[0][lane];
+                for (int k = 1; k < nw; k++)
+                    if (s_cloud[k] == cb) v = lane < 3 ? fminf(v, s_red[k][lane]) : fmaxf(v, s_red[k][lane]);
+                if (lane < 3) atomicMin(bbox + 6 * cb + lane, f2ord(v)); else atomicMax(bbox + 6 * cb + lane, f2ord(v));
+            }
+        } else if (lane < nw && cw >= 0) {
+            int* b = bbox + 6 * cw;
+            atomicMin(b + 0, f2ord(s_red[lane][0])); atomicMin(b + 1, f2ord(s_red[lane][1])); atomicMin(b + 2, f2ord(s_red[lane][2]));
+            atomicMax(b + 3, f2ord(s_red[lane][3])); atomicMax(b + 4, f2ord(s_red[lane][4])); atomicMax(b + 5, f2ord(s_red[lane][5]));
+        }
+    }
+}
 #endif
 
 }  // namespace pcrcg

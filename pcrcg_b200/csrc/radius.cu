@@ -35,28 +35,7 @@ __global__ void k_rbbox_init(int* __restrict__ bbox, int nb)
 __global__ void __launch_bounds__(256) k_rbbox(const float* __restrict__ pts, int n, const int32_t* __restrict__ starts, int nb,
                                                int* __restrict__ bbox)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = i < n;
-    int c = ok ? cloud_of(starts, nb, i) : -1;
-    float v[3] = { 0.f, 0.f, 0.f };
-    if (ok) { v[0] = pts[3 * (size_t)i]; v[1] = pts[3 * (size_t)i + 1]; v[2] = pts[3 * (size_t)i + 2]; }
-    int c0 = __shfl_sync(0xffffffffu, c, 0);
-    if (__all_sync(0xffffffffu, c == c0)) {          // whole warp inside one cloud: reduce first
-        if (c0 < 0) return;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float mn = v[d], mx = v[d];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            }
-            if ((threadIdx.x & 31) == 0) { atomicMin(bbox + 6 * c0 + d, f2ord(mn)); atomicMax(bbox + 6 * c0 + 3 + d, f2ord(mx)); }
-        }
-    } else if (ok) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) { atomicMin(bbox + 6 * c + d, f2ord(v[d])); atomicMax(bbox + 6 * c + 3 + d, f2ord(v[d])); }
-    }
+    bbox_accumulate(pts, n, starts, nb, bbox);
 }
 
 // per cloud: grid origin (support bbox min) and cell edge

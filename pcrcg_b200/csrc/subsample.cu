@@ -33,34 +33,7 @@ __global__ void k_bbox_init(int* __restrict__ bbox, int nb)
 __global__ void __launch_bounds__(256) k_bbox(const float* __restrict__ pts, int n, const int32_t* __restrict__ starts, int nb,
                                               int* __restrict__ bbox)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = i < n;
-    int c = ok ? cloud_of(starts, nb, i) : -1;
-    float x = 0, y = 0, z = 0;
-    if (ok) { x = pts[3 * (size_t)i]; y = pts[3 * (size_t)i + 1]; z = pts[3 * (size_t)i + 2]; }
-    int c0 = __shfl_sync(0xffffffffu, c, 0);
-    if (__all_sync(0xffffffffu, c == c0)) {
-        if (c0 < 0) return;
-        float mnx = x, mny = y, mnz = z, mxx = x, mxy = y, mxz = z;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
-            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-            mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
-        }
-        if ((threadIdx.x & 31) == 0) {
-            int* b = bbox + 6 * c0;
-            atomicMin(b + 0, f2ord(mnx)); atomicMin(b + 1, f2ord(mny)); atomicMin(b + 2, f2ord(mnz));
-            atomicMax(b + 3, f2ord(mxx)); atomicMax(b + 4, f2ord(mxy)); atomicMax(b + 5, f2ord(mxz));
-        }
-    } else if (ok) {
-        int* b = bbox + 6 * c;
-        atomicMin(b + 0, f2ord(x)); atomicMin(b + 1, f2ord(y)); atomicMin(b + 2, f2ord(z));
-        atomicMax(b + 3, f2ord(x)); atomicMax(b + 4, f2ord(y)); atomicMax(b + 5, f2ord(z));
-    }
+    bbox_accumulate(pts, n, starts, nb, bbox);
 }
 
 __device__ __forceinline__ uint64_t f2size_t(float f) { return (uint64_t)(long long)f; }
