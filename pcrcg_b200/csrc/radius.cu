@@ -138,21 +138,21 @@ __device__ __forceinline__ void warp_bitonic(unsigned long long (&v)[R], int lan
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if ((r & jr) == 0) {
-                        const bool asc = ((r * 32) & k) == 0;
-                        unsigned long long a = v[r], b = v[r | jr];
-                        unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
-                        v[r] = asc ? lo : hi;
-                        v[r | jr] = asc ? hi : lo;
+                        const bool asc = ((r * 32) & k) == 0;             // compile-time after unrolling
+                        const unsigned long long a = v[r], b = v[r | jr];
+                        const bool swap = (a < b) != asc;
+                        v[r] = swap ? b : a;
+                        v[r | jr] = swap ? a : b;
                     }
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], j);
-                    const bool asc = (((r * 32) | lane) & k) == 0;
-                    const bool lower = (lane & j) == 0;
-                    const unsigned long long mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
-                    v[r] = (lower == asc) ? mn : mx;
+                    // this lane keeps the smaller key iff (lower half of the pair) == (ascending run); keys are distinct, so
+                    // "take the partner's key" = (mine < partner's) != keep_small: one 64-bit compare and one select per exchange
+                    const bool keep_small = ((lane & j) == 0) == ((((r * 32) | lane) & k) == 0);
+                    v[r] = ((v[r] < o) != keep_small) ? o : v[r];
                 }
             }
         }
