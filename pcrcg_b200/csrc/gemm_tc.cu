@@ -296,7 +296,11 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) k_gemm_bf16x3(const __g
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float v[CH];
 #pragma unroll
-                for (int u = 0; u < CH; u++) v[u] = (__uint_as_float(d[ch & 1][u]) + __uint_as_float(d[ch & 1][CH + u])) * sc;
+                for (int u = 0; u < CH; u++) v[u] = __uint_as_float(d[ch & 1][u]) + __uint_as_float(d[ch & 1][CH + u]);
+                if (row_scale != nullptr) {                   // warp-uniform: the Linears (no row scale) skip the multiplies
+#pragma unroll
+                    for (int u = 0; u < CH; u++) v[u] *= sc;
+                }
                 if (ch + 1 < NCH) {
                     tmem_ld16(trow + (uint32_t)((ch + 1) * CH), d[(ch + 1) & 1]);
                     tmem_ld16(trow + (uint32_t)(BN + (ch + 1) * CH), d[(ch + 1) & 1] + CH);
