@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY: NumPy restatement of the descriptor-matching helpers of the reference
-(lib/benchmark_utils.py).  PARITY UNPINNED for this file: lib/benchmark_utils.py imports open3d (absent here) at module
-level and uses np.bool (removed in NumPy 2), so the reference functions cannot be executed in this container; the
-restatement follows the source line by line instead."""
+(lib/benchmark_utils.py).  The module itself cannot be imported here (open3d at module level, np.bool removed in NumPy 2);
+tests/golden/make_golden.py executes the SOURCE of its four pure functions (to_tensor, to_array, get_inlier_ratio,
+mutual_selection) unchanged, with `np` = NumPy plus the old alias, and tests/test_oracle_pinning.py pins this restatement to
+those outputs (tests/golden/matching_ref.npz)."""
 import numpy as np
 
 

@@ -284,6 +284,42 @@ def main():
     np.savez_compressed(f"{OUT}/point2node_ref.npz", **gn)
     print("point2node: nodes", len(s_nodes), len(t_nodes), "vis mean", float(sv.mean()), float(tv.mean()))
 
+    # ---- descriptor matching (lib/benchmark_utils.py:76-95, 226-295) ----------------------
+    # lib/benchmark_utils.py imports open3d at module level and uses np.bool (removed in NumPy 2): the four pure
+    # functions are taken from its SOURCE with ast and executed unchanged, `np` being NumPy plus the old alias np.bool.
+    class _NumpyWithOldAliases:
+        bool = bool
+
+        def __getattr__(self, k):
+            return getattr(np, k)
+    bu_tree = ast.parse(open(f"{REF}/lib/benchmark_utils.py").read())
+    ns2 = {"torch": torch, "np": _NumpyWithOldAliases()}
+    for node in bu_tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("to_tensor", "to_array", "get_inlier_ratio", "mutual_selection"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "benchmark_utils.py", "exec"), ns2)
+    rng = np.random.default_rng(9)
+    n_s, n_t = 1500, 1300
+    sp_ = rng.uniform(-1, 1, size=(n_s, 3)).astype(np.float32)
+    rot_, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    rot_ = (rot_ * np.sign(np.linalg.det(rot_))).astype(np.float32)
+    trans_ = rng.normal(size=(3, 1)).astype(np.float32)
+    sel = rng.permutation(n_s)[:n_t]
+    tp_ = ((rot_ @ sp_.T + trans_).T)[sel] + rng.normal(scale=0.01, size=(n_t, 3)).astype(np.float32)
+    fs_ = rng.normal(size=(n_s, 32)).astype(np.float32)
+    fs_ /= np.linalg.norm(fs_, axis=1, keepdims=True)
+    ft_ = fs_[sel] + rng.normal(scale=0.22, size=(n_t, 32)).astype(np.float32)
+    ft_ /= np.linalg.norm(ft_, axis=1, keepdims=True)
+    with torch.no_grad():
+        res_ = ns2["get_inlier_ratio"](sp_, tp_, fs_, ft_, rot_, trans_)
+        scores_ = torch.matmul(torch.from_numpy(fs_), torch.from_numpy(ft_).t())
+        mut_ = ns2["mutual_selection"](scores_[None, :, :])[0]
+    r_, c_ = np.where(mut_)
+    gm = dict(src_pcd=sp_, tgt_pcd=tp_, src_feat=fs_, tgt_feat=ft_, rot=rot_, trans=trans_, mutual_rows=r_.astype(np.int64),
+              mutual_cols=c_.astype(np.int64), row_argmax=scores_.max(-1)[1].numpy(),
+              inlier_ratio_wo=np.float32(res_["wo"]["inlier_ratio"]), inlier_ratio_w=np.float32(res_["w"]["inlier_ratio"]))
+    np.savez_compressed(f"{OUT}/matching_ref.npz", **gm)
+    print("matching: mutual pairs", len(r_), "inlier ratios", float(gm["inlier_ratio_wo"]), float(gm["inlier_ratio_w"]))
+
     # ---- projection --------------------------------------------------------------------------
     from projection import Projection
     gp = {}

@@ -1,5 +1,5 @@
 """GPU: descriptor matching front-end and the tester's per-pair .pth file ('next' row 4) vs the NumPy restatement of
-lib/benchmark_utils.py (oracle/matching_port.py; that reference file cannot run here, see its header).  Index lists must
+lib/benchmark_utils.py (oracle/matching_port.py, pinned to the reference's own functions through tests/golden/matching_ref.npz).  Index lists must
 be identical except where two scores tie to within fp32 summation-order noise (reported, bounded)."""
 import numpy as np
 import pytest
@@ -71,3 +71,20 @@ def test_inlier_ratio_and_pair_file(tmp_path):
     assert all(not back[k].is_cuda for k in ("pcd", "feats", "overlaps", "saliency", "rot", "trans"))
     assert torch.equal(back["feats"], feats.cpu()) and back["pcd"].shape == (2 * n, 3)
     assert matching.load_pair(path)["len_src"] == n
+
+
+def test_matching_vs_reference_golden():
+    """mutual pairs, row-wise best matches and both inlier ratios vs the outputs of the reference's own get_inlier_ratio /
+    mutual_selection (tests/golden/matching_ref.npz)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "matching_ref.npz"))
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    idx = matching.best_match(d(g["src_feat"]), d(g["tgt_feat"])).cpu().numpy()
+    assert (idx != g["row_argmax"]).sum() <= 1                      # an fp32 summation-order tie at most
+    rows, cols = matching.mutual_matches(d(g["src_feat"]), d(g["tgt_feat"]))
+    got = set(zip(rows.cpu().tolist(), cols.cpu().tolist()))
+    want = set(zip(g["mutual_rows"].tolist(), g["mutual_cols"].tolist()))
+    assert len(got ^ want) <= 2
+    res = matching.inlier_ratio(d(g["src_pcd"]), d(g["tgt_pcd"]), d(g["src_feat"]), d(g["tgt_feat"]), d(g["rot"]), d(g["trans"]))
+    assert abs(float(res["wo"]["inlier_ratio"]) - float(g["inlier_ratio_wo"])) < 2e-3
+    assert abs(float(res["w"]["inlier_ratio"]) - float(g["inlier_ratio_w"])) < 2e-3

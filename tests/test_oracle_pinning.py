@@ -233,3 +233,12 @@ def test_point2node_port_vs_reference_golden():
                                                    torch.from_numpy(g["corr"]))
     assert np.array_equal(si.numpy(), g["src_idx"]) and np.array_equal(ti.numpy(), g["tgt_idx"])
     assert np.array_equal(sv.numpy(), g["src_node_vis"]) and np.array_equal(tv.numpy(), g["tgt_node_vis"])
+
+
+def test_matching_port_vs_reference_golden():
+    from oracle import matching_port as mp
+    g = np.load(os.path.join(G, "matching_ref.npz"))
+    r, c = mp.mutual_matches(g["src_feat"], g["tgt_feat"])
+    assert np.array_equal(r, g["mutual_rows"]) and np.array_equal(c, g["mutual_cols"])
+    wo, w = mp.inlier_ratios(g["src_pcd"], g["tgt_pcd"], g["src_feat"], g["tgt_feat"], g["rot"], g["trans"])
+    assert abs(wo - float(g["inlier_ratio_wo"])) < 1e-6 and abs(w - float(g["inlier_ratio_w"])) < 1e-6
