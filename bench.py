@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core contraction")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="library A/B switch (pcrcg_set_option), e.g. kpconv_fused=0; repeatable")
     args = ap.parse_args()
     W = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     K = max(args.steps, 1)
@@ -301,6 +303,10 @@ def main():
     L = lib()
     if args.simt:
         ops.force_simt_contraction(True)
+    for o in args.option:
+        name, val = o.split("=")
+        if L.pcrcg_set_option(name.encode(), int(val)) != 0:
+            raise SystemExit(L.pcrcg_last_error().decode())
 
     P = args.pairs
     pairs = make_pairs(args.workload, P, rank * P)                  # pair index sharded by rank
@@ -391,7 +397,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         kernels = {}
         agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
-               "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"]}
+               "kpconv_fused": ["kpconv_fused"], "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"]}
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, parts in agg.items():
             ms = sum(prof[p][0] for p in parts if p in prof) / K

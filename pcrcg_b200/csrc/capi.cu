@@ -69,6 +69,7 @@ void kpconv_set_agg_simt(int);
 void kpconv_set_agg_pipelined(int);
 void kpconv_set_small_fused(int);
 void kpconv_set_chunk_mb(int);
+void kpconv_set_fused(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
@@ -118,7 +119,7 @@ uint64_t pcrcg_launch_count(void) { return g_launches; }
 int32_t pcrcg_profile_classes(void) { return PC_COUNT; }
 const char* pcrcg_profile_class_name(int32_t c)
 {
-    static const char* names[PC_COUNT] = { "subsample", "radius_build", "radius_query", "kpconv_aggregate", "gemm", "norm_act", "pool", "projection" };
+    static const char* names[PC_COUNT] = { "subsample", "radius_build", "radius_query", "kpconv_aggregate", "gemm", "norm_act", "pool", "projection", "kpconv_fused" };
     return (c >= 0 && c < PC_COUNT) ? names[c] : "?";
 }
 // Synchronises the device, sums elapsed ms and scope counts per class, clears the records.
@@ -273,6 +274,7 @@ int pcrcg_set_option(const char* name, int32_t value)
     else if (!strcmp(name, "aggregate_pipelined")) kpconv_set_agg_pipelined(value);
     else if (!strcmp(name, "first_layer_fused")) kpconv_set_small_fused(value);
     else if (!strcmp(name, "kpconv_chunk_mb")) kpconv_set_chunk_mb(value);
+    else if (!strcmp(name, "kpconv_fused")) kpconv_set_fused(value);
     else if (!strcmp(name, "stats_debug")) gemm_set_stats_dbg(value);
     else if (!strcmp(name, "norm_variant")) dense_set_norm_variant(value);
     else if (!strcmp(name, "norm_vectorised")) dense_set_norm_v4(value);

@@ -16,13 +16,10 @@
 //   k_kpconv_aggregate_mma64   fp32 features, cin % 64 == 0: cp.async staging + mma.sync m16n8k8 3xTF32
 //   k_kpconv_aggregate_mma     fp32 features, cin % 8 == 0: direct gathers + 3xTF32
 //   k_kpconv_aggregate         CUDA-core fallback for ragged cin (129: colour path) and the "aggregate_simt" parity anchor
-#include "common.cuh"
-
-#include <cuda_bf16.h>
+#include "agg_ptx.cuh"
 
 namespace pcrcg {
 
-constexpr int KP_MAX = 16;          // kernel points padded to 16
 constexpr int AGG_WARPS = 8;
 
 // flag[s] = (sum_c x[s,c] > 0)      models/blocks.py:369-370 (per support row, shared by all queries)
@@ -670,42 +667,8 @@ static bool launch_small_fused(const float* q_pts, int nq, const float* s_pts, i
 //   A (influence weights, split hi/lo in registers) x B (feature planes hi / lo):  hi*hi + hi*lo + lo*hi
 constexpr int AB_WARPS = 4;
 constexpr int AB_ROWS = 32;                    // neighbours staged per chunk = 2 k-steps of 16
-constexpr int AB_PITCH = 144;                  // bytes per staged plane row (128 + 16: conflict-free ldmatrix)
 constexpr int AB_WARP_BYTES = 2 * AB_ROWS * AB_PITCH + AB_ROWS * 16;    // hi plane, lo plane, coordinates
 constexpr int AB_SMEM = AB_WARPS * AB_WARP_BYTES;
-
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
-{
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
-{
-    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
-}
-// Splits two fp32 values into packed bf16 (hi, lo) pairs (low half = a, high half = b) WITHOUT conversion instructions:
-// hi = the upper 16 bits of the float (truncation), lo = the upper 16 bits of the exact residual x - hi.  hi + lo keeps
-// >= 15 mantissa bits (error <= 2^-16 |x|, of the same order as the lo*lo term bf16x3 drops); PRMT / LOP3 / FADD run on the
-// full-rate pipes where F2F (one per value and rounding step, 112 per point before) is quarter-rate.
-__device__ __forceinline__ uint32_t pack_split(float a, float b, uint32_t& lo_packed)
-{
-    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-    const float ra = a - __uint_as_float(ua & 0xffff0000u), rb = b - __uint_as_float(ub & 0xffff0000u);
-    lo_packed = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
-    return __byte_perm(ua, ub, 0x7632);
-}
 
 template <typename IdxT>
 __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
@@ -869,9 +832,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
 //                   the buffer just consumed as scratch)
 // The neighbour indices (and row flags) of the NEXT point are requested when the current point starts.  Shared memory
 // per warp is unchanged (2 buffers x 16 rows instead of 1 x 32), so residency stays at 5 CTAs / SM.
-constexpr int ABP_ROWS = 16;
-constexpr int ABP_BUF_BYTES = 2 * ABP_ROWS * AB_PITCH;                        // hi + lo rows of one k-step (= stmatrix scratch)
-constexpr int ABP_WARP_BYTES = 2 * ABP_BUF_BYTES + 2 * ABP_ROWS * 16;         // two buffers + two coordinate blocks
 constexpr int ABP_SMEM = AB_WARPS * ABP_WARP_BYTES;
 
 template <typename IdxT>
@@ -1102,6 +1062,15 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
 // first_layer_fused: measured on B200 at 1.33 ms per 32-pair step against 0.88 + 0.31 ms for aggregate_small + the CUDA-core
 // contraction (one short-lived block per 32 points: latency-bound behind its staging barrier) -> opt-in until it is persistent
 static int g_agg_simt = 0, g_agg_pipelined = 1, g_small_fused = 0;
+// kpconv_fused (kpconv_fused.cu): 0 = never, 1 = where it wins (cin == cout == 64: the weights fit tensor memory in one
+// pass), 2 = every shape it supports (cin, cout multiples of 64: S x T passes; parity tests and measurements)
+static int g_fused = 1;
+void kpconv_set_fused(int v) { g_fused = v; }
+bool kpconv_fused_shape_ok(int64_t nq, int64_t ns, int H, int cin, int cout, int K, int ldxs);
+int kpconv_fused_dev(const float* q_pts, int64_t nq, const float* s_pts, int64_t ns, const void* idx, int idx_is_i64, int H, int idx_stride,
+                     const void* x_hi, const void* x_lo, int cin, int ldxs, const uint8_t* rowflag, const float* kpts, int K, float inv_extent,
+                     const void* w_hi, const void* w_lo, int ldk, float* out, int cout, const int32_t* seg_starts, int nseg, double* stats_acc,
+                     int64_t row0, cudaStream_t st);
 void kpconv_set_small_fused(int v) { g_small_fused = v; }
 void kpconv_set_agg_simt(int v) { g_agg_simt = v; }
 void kpconv_set_agg_pipelined(int v) { g_agg_pipelined = v; }
@@ -1223,20 +1192,26 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     __nv_bfloat16* b_lo = b_hi + (size_t)cout * ldk;
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
     const float inv_extent = 1.0f / kp_extent;
-    {
+    if (ns > 0 && rowflag_in == nullptr) {
         ProfScope prof(PC_KPCONV_AGG, st, 1);
-        if (ns > 0 && rowflag_in == nullptr) {
-            k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag_ws);
-            PCRCG_CUDA(cudaGetLastError());
-        }
+        k_row_positive<<<(unsigned)cdiv64(ns, 8), 256, 0, st>>>(x, (int)ns, cin, cin, rowflag_ws);
+        PCRCG_CUDA(cudaGetLastError());
     }
     // which aggregation kernel runs (the same for every chunk): bf16 planes -> ldmatrix kernels; the pipelined one writes its
     // 64-channel slabs in kperm64 order, so the weights are split with the matching K permutation
     const bool planes = tc && x_hi != nullptr && x_lo != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 && !g_agg_simt && ns > 0;
     const bool pipelined = planes && g_agg_pipelined && H <= 64;
+    const bool fused = pipelined && g_fused > 0 && kpconv_fused_shape_ok(nq, ns, H, cin, cout, K, ldxs) &&
+                       (g_fused > 1 || (cin == 64 && cout == 64));
     if (tc) {
-        ProfScope prof(PC_GEMM, st, 0);
+        ProfScope prof(fused ? PC_KPCONV_FUSED : PC_GEMM, st, 0);
         PCRCG_TRY(gemm_tc_split_b_perm_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, pipelined ? 1 : 0, st));
+    }
+    if (fused) {
+        // gather -> influence -> tcgen05 contraction in one kernel: the aggregate stays on the SM
+        ProfScope prof(PC_KPCONV_FUSED, st, 0);
+        return kpconv_fused_dev(q_pts, nq, s_pts, ns, idx, idx_is_i64, H, idx_stride, x_hi, x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, b_hi,
+                                b_lo, ldk, out, cout, seg_starts, nseg, stats_acc, 0, st);
     }
     const size_t idx_bytes = idx_is_i64 ? 8 : 4;
     if (cin <= 4 && !g_agg_simt && !gemm_force_simt_get() && stats_acc == nullptr && ns > 0 && g_small_fused) {
