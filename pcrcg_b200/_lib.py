@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcrcg_b200.so")
+# PCRCG_B200_LIB: another build of the same library (kernel A/B experiments under tools/); never a different implementation
+LIB_PATH = os.environ.get("PCRCG_B200_LIB") or os.path.join(_HERE, "libpcrcg_b200.so")
 
 _lib = None
 

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
     auto accempty_bar = [&](int a) { return bar_base + 8u * (2 * FZ_SLOTS + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * FZ_SLOTS + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+    int* next_point = reinterpret_cast<int*>(base_ptr + (tmem_slot + 8u - base));      // next unclaimed point of this CTA's sequence
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (nq + FZ_TILE - 1) / FZ_TILE;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
 
     if (warp == FZ_FIRST_PW - 1) {
         if (lane == 0) {
+            *next_point = 0;
             for (int s = 0; s < FZ_SLOTS; s++) { mbar_init(full_bar(s), FZ_TILE); mbar_init(empty_bar(s), 1); }
             for (int a = 0; a < 2; a++) { mbar_init(accfull_bar(a), 1); mbar_init(accempty_bar(a), 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,8 +140,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
         const uint32_t dst_off = (uint32_t)(plane * ABP_ROWS * AB_PITCH + chunk * 16 + rsel * AB_PITCH);
         const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
 
-        // sequence number m of this warp's points -> query index (>= nq: a padding row of the last tile)
+        // Points are CLAIMED from a per-CTA counter (sequence number m -> row m % 8 of tile m / 8), three per warp in flight
+        // (current, next: indices and query loaded, after next: indices requested).  A static round-robin lets the warps
+        // drift apart until the fast ones sit at the edge of the 3-tile ring all the time (measured: 14 % of the producer
+        // cycles in the slot wait); claimed in order, the points being finished stay within ~2 tiles of each other.
         const int m_end = my_tiles * FZ_TILE;
+        auto claim = [&]() -> int {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(next_point, 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
         auto point_of = [&](int m) -> int { return (((int)blockIdx.x + (m >> 3) * (int)gridDim.x) << 3) + (m & 7); };
         auto load_raw = [&](int m, IdxT& r0, IdxT& r1) {
             const int p = m < m_end ? min(point_of(m), nq - 1) : nq - 1;
@@ -255,7 +265,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
             for (int i2 = 0; i2 < 8; i2++) { acc[i2][0] = acc[i2][1] = acc[i2][2] = acc[i2][3] = 0.f; }
         };
 
-        int m = pw;
+        int m = claim();
+        int nm = claim();
+        (void)pw;
         if (m < m_end) {
             int j0, j1;
             {
@@ -278,11 +290,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
                 put_xyz(0, v, x, y, z, qx, qy, qz);
             }
             IdxT nr0, nr1;
-            load_raw(m + FZ_PW, nr0, nr1);
+            load_raw(nm, nr0, nr1);
             while (m < m_end) {
-                const int nm = m + FZ_PW;
+                const int fm = claim();
                 IdxT fr0, fr1;
-                load_raw(nm + FZ_PW, fr0, fr1);
+                load_raw(fm, fr0, fr1);
                 int nj0 = ns, nj1 = ns;
                 const size_t qo = 3 * (size_t)(nm < m_end ? min(point_of(nm), nq - 1) : 0);
                 const float nqx = q_pts[qo], nqy = q_pts[qo + 1], nqz = q_pts[qo + 2];
@@ -333,6 +345,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
                 const int cnt = __popc(__ballot_sync(0xffffffffu, j0 < ns && f0 != 0)) + __popc(__ballot_sync(0xffffffffu, j1 < ns && f1 != 0));
                 store_point(m, 1.0f / (float)(cnt > 1 ? cnt : 1));
                 m = nm;
+                nm = fm;
                 j0 = nj0; j1 = nj1;
                 nr0 = fr0; nr1 = fr1;
                 qx = nqx; qy = nqy; qz = nqz;
