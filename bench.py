@@ -95,7 +95,9 @@ def cpu_reference_run(pairs, cfg, limits, state_dict, threads):
     import torch
     import oracle
     from oracle import blocks_port as bp
-    kind = "reference" if oracle.have_ref() else "port"
+    # subsample / search: the unmodified reference C++ (oracle/_ref) when built; the encoder is ALWAYS the PyTorch-CPU
+    # restatement oracle/blocks_port.py (the reference's models/blocks.py cannot travel to the GPU box)
+    kind = ("reference C++ (subsample, search)" if oracle.have_ref() else "port (subsample, search)") + " + port (PyTorch-CPU encoder)"
     torch.set_num_threads(threads)
     blocks_desc = bp.encoder_blocks_from_state_dict({k: v.cpu() for k, v in state_dict.items()}, prefix="encoder_blocks.",
                                                     first_subsampling_dl=cfg.first_subsampling_dl, conv_radius=cfg.conv_radius,
@@ -215,6 +217,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="fragment pairs per step per GPU")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-pair", type=int, default=0, help="pair of the batch checked against the oracle (outside the timed regions)")
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core contraction")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="library A/B switch (pcrcg_set_option), e.g. kpconv_fused=0; repeatable")
@@ -330,6 +334,20 @@ def main():
         path.run_host(pts_host, lens_host, out_bufs[i])
     work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder)
 
+    # ---- parity of THIS batch, outside every timed region: one pair of the stacked run vs the reference run on that pair
+    # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        from oracle import checks
+        kq = min(args.parity_pair, P - 1)
+        cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
+        n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
+        seg = batch["pair_segments"][-1].cpu().tolist()
+        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg)
+        parity = {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
+                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "ok": (not bad) and enc_err < 1e-3,
+                  "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
+
     # ---- device-resident timed region ----------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -436,6 +454,8 @@ def main():
                 "gpu_launches": launches, "roofline": roof, "kernels": kernels}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
