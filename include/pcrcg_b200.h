@@ -68,6 +68,16 @@ int pcrcg_radius_build_dev(const float* supports, int64_t ns, const int32_t* s_l
 int pcrcg_radius_query_dev(const float* queries, int64_t nq, const int32_t* q_lens, int64_t ns, int32_t nb, float radius,
                            int32_t width, int32_t row_stride, int32_t* rows, int32_t* counts, int32_t* max_count,
                            void* ws, size_t ws_bytes, pcrcg_stream_t stream);
+/* Step 2, cell-centric (the default of the Python layer): one warp per occupied query cell; the 27 adjacent support cells
+ * are resolved and their records staged in shared memory once per cell, every query of the cell tests the staged candidates.
+ * queries_are_supports != 0: `queries` is the point set the grid was built from (conv lists; qws unused).  Otherwise the
+ * queries are first binned into the support grid's cells inside qws (pcrcg_radius_query_ws_bytes(nq, nb) bytes).  Same
+ * results as pcrcg_radius_query_dev, bit for bit. */
+size_t pcrcg_radius_query_ws_bytes(int64_t nq, int32_t nb);
+int pcrcg_radius_query_cells_dev(const float* queries, int64_t nq, const int32_t* q_lens, int64_t ns, int32_t nb, float radius,
+                                 int32_t width, int32_t row_stride, int32_t* rows, int32_t* counts, int32_t* max_count,
+                                 void* ws, size_t ws_bytes, void* qws, size_t qws_bytes, int32_t queries_are_supports,
+                                 pcrcg_stream_t stream);
 /* Host buffers in; *out_rows is malloc'ed [nq,*out_width] with *out_width = max_count when limit<=0
  * (the reference's output) or min(limit, max_count). */
 int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* supports, int64_t ns, const int32_t* q_lens,
@@ -127,6 +137,8 @@ int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* 
 void pcrcg_gemm_force_simt(int32_t on);
 /* A/B switches for measurements: "contraction_simt", "aggregate_simt" (CUDA-core variants of the two KPConv stages),
  * "aggregate_pipelined" (persistent software-pipelined bf16 aggregation, default 1; 0 = one point per warp),
+ * "kpconv_fused" (0 = two-kernel KPConv everywhere, 1 = one-kernel KPConv for cin == cout == 64 (default), 2 = for every
+ * cin, cout multiple of 64),
  * "kpconv_chunk_mb" (bound of one KPConv intermediate buffer in MiB, 0 = default 8192; query rows beyond it are processed in chunks),
  * "first_layer_fused" (cin <= 4: aggregation + contraction in one kernel; default 0, the two-kernel path measures faster),
  * "norm_vectorised" (float4 InstanceNorm apply kernel, default 1), "norm_variant" (0 = per-mode launch shape, 1..4 fixed),

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pcrcg_radius_ws_bytes": (_SZ, [_I64, _I64, _I32]),
     "pcrcg_radius_build_dev": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _SZ, _P]),
     "pcrcg_radius_query_dev": (C.c_int, [_P, _I64, _P, _I64, _I32, _F, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "pcrcg_radius_query_ws_bytes": (_SZ, [_I64, _I32]),
+    "pcrcg_radius_query_cells_dev": (C.c_int, [_P, _I64, _P, _I64, _I32, _F, _I32, _I32, _P, _P, _P, _P, _SZ, _P, _SZ, _I32, _P]),
     "pcrcg_batch_query_host": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _I32, _F, _I32, C.POINTER(_P), C.POINTER(_I32)]),
     "pcrcg_kpconv_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "pcrcg_kpconv_forward_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _F, _P, _I32, _P, _P, _SZ, _P]),

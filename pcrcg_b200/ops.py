@@ -60,7 +60,8 @@ class RadiusGrid:
                                            self.ws.data_ptr(), self.ws.numel(), _stream()))
 
     def query(self, queries, q_lens, width, want_counts=True):
-        """-> rows [Nq,width] i32 (None if width == 0), counts [Nq] i32, max_count [1] i32 (device)."""
+        """-> rows [Nq,width] i32 (None if width == 0), counts [Nq] i32, max_count [1] i32 (device).
+        Cell-centric search (pcrcg_radius_query_cells_dev); ``cell_centric(False)`` selects the one-warp-per-query kernel."""
         _need_cuda(queries, q_lens)
         queries, q_lens = _f32c(queries), _i32c(q_lens)
         nq = queries.shape[0]
@@ -70,11 +71,28 @@ class RadiusGrid:
             rows = torch.empty((nq, width), dtype=torch.int32, device=dev) if width > 0 else None
             counts = torch.empty(nq, dtype=torch.int32, device=dev) if want_counts else None
             mx = torch.zeros(1, dtype=torch.int32, device=dev)
-            check(L.pcrcg_radius_query_dev(queries.data_ptr(), nq, q_lens.data_ptr(), self.ns, self.nb, self.radius,
-                                           int(width), int(width), rows.data_ptr() if rows is not None else None,
-                                           counts.data_ptr() if counts is not None else None, mx.data_ptr(),
-                                           self.ws.data_ptr(), self.ws.numel(), _stream()))
+            rp = rows.data_ptr() if rows is not None else None
+            cp = counts.data_ptr() if counts is not None else None
+            if _cell_centric:
+                same = queries.data_ptr() == self.supports.data_ptr() and nq == self.ns
+                qws = None if same else _ws(L.pcrcg_radius_query_ws_bytes(nq, self.nb), dev)
+                check(L.pcrcg_radius_query_cells_dev(queries.data_ptr(), nq, q_lens.data_ptr(), self.ns, self.nb, self.radius,
+                                                     int(width), int(width), rp, cp, mx.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                                     qws.data_ptr() if qws is not None else None, qws.numel() if qws is not None else 0,
+                                                     1 if same else 0, _stream()))
+            else:
+                check(L.pcrcg_radius_query_dev(queries.data_ptr(), nq, q_lens.data_ptr(), self.ns, self.nb, self.radius,
+                                               int(width), int(width), rp, cp, mx.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream()))
         return rows, counts, mx
+
+
+_cell_centric = True
+
+
+def cell_centric(on):
+    """A/B switch of the radius search kernel (True: one warp per occupied query cell, False: one warp per query)."""
+    global _cell_centric
+    _cell_centric = bool(on)
 
 
 def batch_query(queries, supports, q_lens, s_lens, radius, limit=0):

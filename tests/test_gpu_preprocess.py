@@ -204,6 +204,37 @@ def test_radius_counts_and_symmetry_full_size():
     assert (np.diff(d, axis=1) >= -1e-7).all()
 
 
+@pytest.mark.parametrize("limit", [34, 80, 0])
+def test_radius_cell_centric_equals_per_query_kernel(limit):
+    """the cell-centric search (default) and the one-warp-per-query kernel give the same rows, counts and max count, for
+    Q == S (the support cells are the work units), Q != S (queries binned into the support grid) and both capacity
+    configurations (list width <= 48 / wider)"""
+    src, tgt, _ = synthetic.match3d_pair(2, n_target=6000)
+    pts, lens = _stack([src, tgt, src[:1], tgt[:0] if False else tgt[:3]])
+    P, L = _t(pts), _t(lens)
+    sub, sl = ops.subsample_batch(P, L, 0.05)
+    far = torch.cat([sub[:50] + 3.0, sub[:50] - 3.0])                       # queries outside the supports' bounding box
+    cases = [(P, L, P, L, 0.0625), (sub, sl, P, L, 0.0625), (P, L, sub, sl, 0.125),
+             (torch.cat([far, sub]), torch.cat([torch.tensor([100], dtype=torch.int32, device=DEV) + sl[:1], sl[1:]]), P, L, 0.0625)]
+    for q, ql, s, sl_, rad in cases:
+        g = ops.RadiusGrid(s, sl_, rad)
+        out = {}
+        for mode in (True, False):
+            ops.cell_centric(mode)
+            try:
+                if limit == 0:
+                    _, c, mx = g.query(q, ql, 0)
+                    rows, c2, _ = g.query(q, ql, int(mx.item()))
+                else:
+                    rows, c, mx = g.query(q, ql, limit)
+                out[mode] = (rows.cpu().numpy(), c.cpu().numpy(), int(mx.item()))
+            finally:
+                ops.cell_centric(True)
+        assert out[True][2] == out[False][2]
+        assert np.array_equal(out[True][1], out[False][1])
+        assert np.array_equal(out[True][0], out[False][0])
+
+
 def test_radius_errors():
     z = np.zeros((4, 3), np.float32)
     with pytest.raises(RuntimeError, match=r"query.shape is not \(N, 3\)"):
