@@ -28,6 +28,35 @@ def _ws(nbytes, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
+# Derived data that rides on a tensor as Python attributes (the bf16 planes of its values, its InstanceNorm statistics, its
+# row-positive flags) is stamped with the tensor's version counter and ignored once an in-place update has changed the
+# values.  Ops of this module that write in place through the C library (which the counter does not see) strip it.
+_DERIVED = ("_pcrcg_stats", "_pcrcg_split", "_pcrcg_rowpos")
+
+
+def _attach(t, name, value):
+    setattr(t, name, (value, t._version))
+
+
+def _attached(t, name):
+    if isinstance(t, PlaneTensor):
+        return getattr(t, name, None)
+    v = getattr(t, name, None)
+    if v is None:
+        return None
+    value, version = v
+    return value if version == t._version else None
+
+
+attached = _attached          # public: derived data of a tensor if still valid (tests, diagnostics)
+
+
+def _strip_derived(t):
+    for name in _DERIVED:
+        if hasattr(t, name):
+            delattr(t, name)
+
+
 def subsample_batch(points, lens, sampleDl, max_p=0):
     """points [N,3] f32 cuda, lens [B] i32 cuda -> (s_points [M,3], s_lens [B] i32 cuda).
     One host sync (to learn M)."""
@@ -144,7 +173,7 @@ def _stats_end(out, seg, acc, eps=1e-5):
     mean = torch.empty((nseg, c), dtype=torch.float32, device=out.device)
     rstd = torch.empty((nseg, c), dtype=torch.float32, device=out.device)
     check(lib().pcrcg_colstats_final_dev(acc.data_ptr(), seg.data_ptr(), nseg, c, float(eps), mean.data_ptr(), rstd.data_ptr(), _stream()))
-    out._pcrcg_stats = (mean, rstd, seg, float(eps))
+    _attach(out, "_pcrcg_stats", (mean, rstd, seg, float(eps)))
 
 
 def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_extent, stat_segments=False):
@@ -169,14 +198,14 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
     with torch.cuda.device(dev):
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         ws = _ws(L.pcrcg_kpconv_ws_bytes(nq, ns, cin, K), dev)
-        sp = getattr(x, "_pcrcg_split", None)
+        sp = _attached(x, "_pcrcg_split")
         xptr = None if planes else x.data_ptr()
         seg, acc = _stats_begin(nq, cout, stat_segments, dev)
         if planes and (acc is None or K * cin < 16):
             raise RuntimeError("kpconv_forward: planes-only features need the tensor-core path")
         if acc is not None and K * cin >= 16:
             hi, lo, ld = sp if sp is not None else (None, None, 0)
-            rp = getattr(x, "_pcrcg_rowpos", None) if sp is not None else None
+            rp = _attached(x, "_pcrcg_rowpos") if sp is not None else None
             check(L.pcrcg_kpconv_forward_stats_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
                                                    xptr, hi.data_ptr() if hi is not None else None,
                                                    lo.data_ptr() if lo is not None else None, ld,
@@ -186,7 +215,7 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
             _stats_end(out, seg, acc)
         elif sp is not None and not _force_simt:
             hi, lo, ld = sp
-            rp = getattr(x, "_pcrcg_rowpos", None)
+            rp = _attached(x, "_pcrcg_rowpos")
             check(L.pcrcg_kpconv_forward_split_dev(q_pts.data_ptr(), nq, s_pts.data_ptr(), ns, idx.data_ptr(), is64, H, stride,
                                                    x.data_ptr(), hi.data_ptr(), lo.data_ptr(), ld,
                                                    rp.data_ptr() if rp is not None else None, cin, kernel_points.data_ptr(), K,
@@ -222,7 +251,7 @@ def linear(x, weight, stat_segments=False):
     n, cin = x.shape
     out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
     L = lib()
-    sp = getattr(x, "_pcrcg_split", None)
+    sp = _attached(x, "_pcrcg_split")
     with torch.cuda.device(x.device):
         if sp is not None and not _force_simt and cout % 16 == 0 and cin >= 16 and n >= 1:
             hi, lo, ld = sp
@@ -291,7 +320,7 @@ class PlaneTensor:
 
 def _stats_of(x, segments, eps):
     """statistics attached by the producing contraction (same eps, same segment tensor) or a pass over x"""
-    st = getattr(x, "_pcrcg_stats", None)
+    st = _attached(x, "_pcrcg_stats")
     if st is not None and st[3] == float(eps) and x.dtype == torch.float32 and x.is_contiguous():
         mean, rstd, seg, _ = st
         if (segments is None and seg.shape[0] == 2) or (segments is not None and seg.data_ptr() == _i32c(segments).data_ptr()):
@@ -329,9 +358,9 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
     if planes_only:
         return PlaneTensor(sp[0], sp[1], sp[2], n, c, rp)
     if sp is not None:
-        out._pcrcg_split = sp
+        _attach(out, "_pcrcg_split", sp)
     if rp is not None:
-        out._pcrcg_rowpos = rp
+        _attach(out, "_pcrcg_rowpos", rp)
     return out
 
 
@@ -453,6 +482,7 @@ def bias_act(x, bias, slope=None, out=None):
     x = _f32c(x)
     n, c = x.shape
     out = torch.empty_like(x) if out is None else out
+    _strip_derived(out)                                   # in place: planes / statistics of the old values are stale
     with torch.cuda.device(x.device):
         check(lib().pcrcg_bias_act_dev(x.data_ptr(), n, c, bias.data_ptr() if bias is not None else None,
                                        -1.0 if slope is None else float(slope), out.data_ptr(), _stream()))
@@ -463,6 +493,7 @@ def softmax_rows_(x, scale=1.0):
     """in place: x <- softmax(scale * x, dim=1)"""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    _strip_derived(x)
     with torch.cuda.device(x.device):
         check(lib().pcrcg_softmax_rows_dev(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), float(scale), _stream()))
     return x

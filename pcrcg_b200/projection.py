@@ -14,6 +14,9 @@ from ._lib import lib, check
 from .ops import _f32c, _stream, _ws
 
 
+MAX_VIEWS = 8                     # csrc/projection.cu: ViewSet
+
+
 def _mat16(m):
     m = torch.as_tensor(m, dtype=torch.float32).detach().cpu()
     if tuple(m.shape) == (3, 3):                      # projection.py:22-25
@@ -55,12 +58,15 @@ def unproject_features(points, views, base=None, thresh=0.1):
 
     points [N,3] cuda; views: list in the reference's WRITE order (e.g. src image 2, src image 1,
     tgt image 2, tgt image 1) of dicts with ``depth`` [H,W], ``world2camera`` [4,4], ``intrinsics``
-    [4,4], ``feature2d`` [C,H,W] (cuda), optional ``valid_map`` [H,W], and ``rows`` = (lo, hi): the
-    range of point rows (the cloud) the view belongs to.  Returns x [N, C+1]."""
+    [4,4], ``feature2d`` [C,H,W] (cuda), optional ``valid_map`` [H,W] (the reference batch's [W,H] layout is accepted
+    and transposed; a square map is taken as [H,W]), and ``rows`` = (lo, hi): the range of point rows (the cloud) the
+    view belongs to.  All views share one (C, H, W); at most 8 views per call.  Returns x [N, C+1]."""
     pts = _f32c(points)
     dev = pts.device
     n = pts.shape[0]
     nv = len(views)
+    if not 1 <= nv <= MAX_VIEWS:
+        raise RuntimeError(f"unproject_features: between 1 and {MAX_VIEWS} views per call (got {nv})")
     keep = []
     dptr, fptr, vptr = (C.c_void_p * nv)(), (C.c_void_p * nv)(), (C.c_void_p * nv)()
     w2c = np.zeros((nv, 16), np.float32)
@@ -71,13 +77,32 @@ def unproject_features(points, views, base=None, thresh=0.1):
         d = _f32c(torch.as_tensor(view["depth"]).to(dev))
         d = d.reshape(d.shape[-2], d.shape[-1])
         f = _f32c(torch.as_tensor(view["feature2d"]).to(dev))
+        if f.dim() != 3:
+            raise RuntimeError(f"unproject_features: view {v}: feature2d must be [C,H,W], got {tuple(f.shape)}")
+        if Cc is None:
+            Cc, H, W = f.shape
+        # the kernel indexes every view with ONE (C, H, W): a view of another size would read out of bounds
+        if tuple(f.shape) != (Cc, H, W):
+            raise RuntimeError(f"unproject_features: view {v}: feature2d {tuple(f.shape)} differs from view 0's {(Cc, H, W)}")
+        if tuple(d.shape) != (H, W):
+            raise RuntimeError(f"unproject_features: view {v}: depth {tuple(d.shape)} does not match feature2d's (H, W) = {(H, W)}")
         vm = view.get("valid_map")
-        vm = _f32c(torch.as_tensor(vm).to(dev)) if vm is not None else None
+        if vm is not None:
+            vm = torch.as_tensor(vm).to(dev)
+            vm = vm.reshape(vm.shape[-2], vm.shape[-1])
+            if tuple(vm.shape) == (W, H) and H != W:
+                # the reference batch stores valid maps as [W,H] and transposes them in KPFCNN.forward
+                # (models/architectures.py:287-307): accept that layout as is
+                vm = vm.t()
+            if tuple(vm.shape) != (H, W):
+                raise RuntimeError(f"unproject_features: view {v}: valid_map {tuple(vm.shape)} is neither (H, W) = {(H, W)} nor (W, H)")
+            vm = _f32c(vm)
         keep += [d, f, vm]
-        Cc, H, W = f.shape
         dptr[v], fptr[v], vptr[v] = d.data_ptr(), f.data_ptr(), (vm.data_ptr() if vm is not None else None)
         w2c[v], k4[v] = _mat16(view["world2camera"]), _mat16(view["intrinsics"])
         lo[v], hi[v] = view.get("rows", (0, n))
+        if not 0 <= lo[v] <= hi[v] <= n:
+            raise RuntimeError(f"unproject_features: view {v}: rows {(int(lo[v]), int(hi[v]))} outside [0, {n}]")
     out = torch.empty((n, Cc + 1), dtype=torch.float32, device=dev)
     b = _f32c(base.reshape(-1)) if base is not None else None
     with torch.cuda.device(dev):

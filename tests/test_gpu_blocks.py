@@ -227,7 +227,7 @@ def test_kpconv_shadow_steps_anywhere_and_epilogue_statistics():
         assert _err(out, ref) < 1e-4, name
         if not hasattr(out, "_pcrcg_stats"):       # fp32 CUDA-core contraction (parity anchor): separate statistics pass
             continue
-        mean, rstd, _, _ = out._pcrcg_stats
+        mean, rstd, _, _ = ops.attached(out, "_pcrcg_stats")
         for k in range(2):
             blk_ = out[int(seg[k]):int(seg[k + 1])].double()
             mu = blk_.mean(0)
@@ -295,5 +295,5 @@ def test_kpconv_chunked_intermediate_equals_unchunked():
         lib().pcrcg_set_option(b"kpconv_chunk_mb", 0)
     assert len(pts) > 3 * 1024 and torch.equal(one, many)
     if hasattr(one, "_pcrcg_stats"):
-        assert torch.allclose(one._pcrcg_stats[0], many._pcrcg_stats[0], rtol=0, atol=1e-6)
-        assert torch.allclose(one._pcrcg_stats[1], many._pcrcg_stats[1], rtol=1e-5, atol=0)
+        assert torch.allclose(ops.attached(one, "_pcrcg_stats")[0], ops.attached(many, "_pcrcg_stats")[0], rtol=0, atol=1e-6)
+        assert torch.allclose(ops.attached(one, "_pcrcg_stats")[1], ops.attached(many, "_pcrcg_stats")[1], rtol=1e-5, atol=0)

@@ -103,9 +103,9 @@ def test_kpconv_support_permutation_invariance_full_size(demo_batch):
         x = ops.instance_norm_act(raw, None, 0.1, emit_split=planes, emit_rowpos=planes)
         xp = x[perm].contiguous()                       # the SAME feature values, rows relabelled (planes and row flags too)
         if planes:
-            hi, lo, ld = x._pcrcg_split
-            xp._pcrcg_split = (hi[perm].contiguous(), lo[perm].contiguous(), ld)
-            xp._pcrcg_rowpos = x._pcrcg_rowpos[perm].contiguous()
+            hi, lo, ld = ops.attached(x, "_pcrcg_split")
+            ops._attach(xp, "_pcrcg_split", (hi[perm].contiguous(), lo[perm].contiguous(), ld))
+            ops._attach(xp, "_pcrcg_rowpos", ops.attached(x, "_pcrcg_rowpos")[perm].contiguous())
         out = ops.kpconv_forward(pts, pts, idx, x, kp, w, 0.05)
         out_p = ops.kpconv_forward(pts, pts[perm], idx_p, xp, kp, w, 0.05)
         assert torch.equal(out, out_p), f"planes={planes}"

@@ -87,11 +87,11 @@ def test_linear_epilogue_statistics(M, N, K, seg):
     hi, lo, ld = ops._split_planes(M, K, x.device)
     from pcrcg_b200._lib import lib, check
     check(lib().pcrcg_split_bf16_dev(x.data_ptr(), K, M, K, hi.data_ptr(), lo.data_ptr(), ld, torch.cuda.current_stream().cuda_stream))
-    x._pcrcg_split = (hi, lo, ld)
+    ops._attach(x, "_pcrcg_split", (hi, lo, ld))
     segt = None if seg is None else torch.tensor(seg, dtype=torch.int32, device=DEV)
     out = ops.linear(x, w, stat_segments=True if segt is None else segt)
     assert hasattr(out, "_pcrcg_stats"), "tensor-core path must attach the statistics"
-    mean, rstd, _, _ = out._pcrcg_stats
+    mean, rstd, _, _ = ops.attached(out, "_pcrcg_stats")
     rm, rr = _ref_stats(out, seg or [0, M])
     assert float((mean.double() - rm).abs().max()) < 1e-5 * float(rm.abs().max().clamp_min(1.0))
     # variance = E[x^2] - mean^2 with fp32 partial sums per 32-row block (as the separate statistics pass): absolute
@@ -102,3 +102,24 @@ def test_linear_epilogue_statistics(M, N, K, seg):
     plain = out.clone()                          # no attribute -> separate statistics pass
     sep = ops.instance_norm_act(plain, segt, 0.1)
     assert float((fused - sep).abs().max()) < 2e-4 * float(sep.abs().max())
+
+
+def test_derived_data_is_dropped_after_an_in_place_update():
+    """bf16 planes / statistics ride on tensors as attributes stamped with the tensor's version: an in-place update of the
+    values (torch's add_, or this module's own in-place bias_act) must not leave stale planes behind"""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(300, 64, generator=g).to(DEV)
+    w = (torch.randn(32, 64, generator=g) / 8.0).to(DEV)
+    y = ops.instance_norm_act(x, None, 0.1, emit_split=True)
+    assert ops.attached(y, "_pcrcg_split") is not None
+    ref0 = ops.linear(y.clone(), w)
+    assert float((ops.linear(y, w) - ref0).abs().max()) < 1e-4 * float(ref0.abs().max())
+    y.add_(1.0)                                            # version bump: the planes describe the old values
+    assert ops.attached(y, "_pcrcg_split") is None
+    ref1 = ops.linear(y.clone(), w)
+    assert float((ops.linear(y, w) - ref1).abs().max()) < 1e-4 * float(ref1.abs().max())
+    z = ops.instance_norm_act(x, None, 0.1, emit_split=True)
+    ops.bias_act(z, torch.ones(64, device=DEV), out=z)     # in place through the library: derived data stripped
+    assert not hasattr(z, "_pcrcg_split")
+    ref2 = ops.linear(z.clone(), w)
+    assert float((ops.linear(z, w) - ref2).abs().max()) < 1e-4 * float(ref2.abs().max())

@@ -57,7 +57,7 @@ def _geometry(seed, n_target, limit, n_pairs=2, strided=False):
 def _run(mode, q, s, rows, xp, kp, w, seg):
     check(lib().pcrcg_set_option(b"kpconv_fused", mode))
     out = ops.kpconv_forward(q, s, rows, xp, kp, w, 0.05, stat_segments=seg)
-    mean, rstd, _, _ = out._pcrcg_stats
+    mean, rstd, _, _ = ops.attached(out, "_pcrcg_stats")
     torch.cuda.synchronize()
     return out, mean, rstd
 

@@ -74,3 +74,27 @@ def test_colour_path_first_block_129_channels():
                           dict(kernel_points=blk.KPConv.kernel_points.cpu(), weights=blk.KPConv.weights.cpu(), KP_extent=0.05))
     err = float((y.cpu() - ref).abs().max() / ref.abs().max())
     assert err < 1e-3
+
+
+def test_unproject_validates_views_and_accepts_reference_valid_map_layout():
+    """every view must share one (C, H, W) (the kernel indexes all of them with it); the reference batch's [W,H] valid maps
+    (transposed inside KPFCNN.forward, models/architectures.py:287-307) are accepted as they are"""
+    src, _, _ = synthetic.match3d_pair(3, n_target=3000)
+    vs = synthetic.rgbd_views(src, 5, n_views=2, channels=16)
+    pts = torch.from_numpy(src).to(DEV)
+    mk = lambda v, **o: dict(v, feature2d=torch.from_numpy(v["feature2d"]).to(DEV), **o)
+    ref = gp.unproject_features(pts, [mk(vs[1]), mk(vs[0])])
+    wh = gp.unproject_features(pts, [mk(vs[1], valid_map=np.ascontiguousarray(vs[1]["valid_map"].T)),
+                                     mk(vs[0], valid_map=np.ascontiguousarray(vs[0]["valid_map"].T))])
+    assert torch.equal(ref, wh)
+    bad_feat = mk(vs[0]); bad_feat["feature2d"] = bad_feat["feature2d"][:, :-1]
+    with pytest.raises(RuntimeError, match="differs from view 0"):
+        gp.unproject_features(pts, [mk(vs[1]), bad_feat])
+    with pytest.raises(RuntimeError, match="depth"):
+        gp.unproject_features(pts, [mk(vs[1], depth=vs[1]["depth"][:-2])])
+    with pytest.raises(RuntimeError, match="valid_map"):
+        gp.unproject_features(pts, [mk(vs[1], valid_map=vs[1]["valid_map"][:, :-3])])
+    with pytest.raises(RuntimeError, match="views per call"):
+        gp.unproject_features(pts, [mk(vs[0])] * 9)
+    with pytest.raises(RuntimeError, match="rows"):
+        gp.unproject_features(pts, [mk(vs[0], rows=(0, len(src) + 1))])
