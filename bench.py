@@ -36,7 +36,7 @@ def make_pairs(workload, n_pairs, seed0):
     from pcrcg_b200 import synthetic
     pairs = []
     for i in range(n_pairs):
-        if workload == "3dmatch":
+        if workload in ("3dmatch", "colour"):
             s, t, _ = synthetic.match3d_pair(seed0 + i)
         elif workload == "3dlomatch":
             s, t, _ = synthetic.match3d_pair(seed0 + i, overlap="low")
@@ -54,8 +54,33 @@ def workload_config(workload):
     from pcrcg_b200 import blocks, pipeline
     if workload == "kitti":
         return blocks.kitti_config(), pipeline.CALIBRATED_LIMITS["kitti_synthetic"]
+    if workload == "colour":           # configs/test/indoor.yaml:34 ships in_feats_dim = 129 (128 image-feature channels + 1)
+        return blocks.indoor_config(in_feats_dim=129), pipeline.CALIBRATED_LIMITS["3dmatch_synthetic"]
     key = "3dmatch_synthetic" if workload == "3dmatch" else "3dlomatch_synthetic"
     return blocks.indoor_config(), pipeline.CALIBRATED_LIMITS[key]
+
+
+def make_views_np(pairs, seed0):
+    """colour workload: per cloud two RGB-D views (depth rendered from the cloud, random stand-in for the 2D backbone's
+    128-channel feature map, valid map), in the reference's write order (image 2, then image 1)."""
+    from pcrcg_b200 import synthetic
+    out = []
+    for i, (s, t) in enumerate(pairs):
+        for j, cloud in enumerate((s, t)):
+            out.append(synthetic.rgbd_views(cloud, 1000 * (seed0 + i) + j, n_views=2, channels=128)[::-1])
+    return out
+
+
+def views_to_device(views_np, device, depth_on_host=False):
+    """Feature / valid maps go to the device (in PCR-CG they are the output of the 2D CNN, which is not part of this path);
+    depth maps either too, or stay in pinned host memory (e2e arm: copied inside the timed region)."""
+    import torch
+    out = []
+    for vs in views_np:
+        out.append([dict(depth=(torch.from_numpy(v["depth"]).pin_memory() if depth_on_host else torch.from_numpy(v["depth"]).to(device)),
+                         world2camera=v["world2camera"], intrinsics=v["intrinsics"], feature2d=torch.from_numpy(v["feature2d"]).to(device),
+                         valid_map=torch.from_numpy(v["valid_map"]).to(device)) for v in vs])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -88,7 +113,20 @@ def _cpu_preprocess(args):
     return out
 
 
-def cpu_reference_run(pairs, cfg, limits, state_dict, threads):
+def cpu_unproject(pair, views2):
+    """oracle/projection_port.py on one pair: views2 = [views of src, views of tgt] in write order -> x [N, 129]"""
+    from oracle import projection_port as pp
+    src, tgt = pair
+    ov, lo = [], 0
+    for cloud, vs in zip((src, tgt), views2):
+        for v in vs:
+            i2, i3 = pp.projection(cloud, v["depth"], v["world2camera"], v["intrinsics"])
+            ov.append((v["feature2d"], v["valid_map"], i2, i3 + lo))
+        lo += len(cloud)
+    return pp.scatter_image_features(len(src) + len(tgt), ov)
+
+
+def cpu_reference_run(pairs, cfg, limits, state_dict, threads, views_np=None):
     """Times the CPU path on `pairs`: preprocessing in worker processes (one pair per core, like the
     reference's DataLoader workers), then the encoder with `threads` torch threads.  -> (pairs/s, kind)"""
     import concurrent.futures as cf
@@ -113,9 +151,11 @@ def cpu_reference_run(pairs, cfg, limits, state_dict, threads):
     t_pre = time.perf_counter() - t0
     t0 = time.perf_counter()
     with torch.no_grad():
-        for p in pyrs:
+        for ip, p in enumerate(pyrs):
             batch = {k: [torch.from_numpy(np.ascontiguousarray(a)) for a in v] for k, v in p.items()}
             x = torch.ones(batch["points"][0].shape[0], cfg.in_feats_dim)
+            if views_np is not None:                      # colour path: projection.py + the scatter of models/architectures.py:360-370
+                x = torch.from_numpy(cpu_unproject(pairs[ip], views_np[2 * ip:2 * ip + 2]))
             bp.encoder(x, batch, blocks_desc)
     t_enc = time.perf_counter() - t0
     return len(pairs) / (t_pre + t_enc), kind, dict(preprocess_s=round(t_pre, 3), encoder_s=round(t_enc, 3), workers=workers)
@@ -168,7 +208,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def algorithmic_work(batch, cfg, limits, enc):
+def algorithmic_work(batch, cfg, limits, enc, views=None):
     """Per-step algorithmic bytes / flops per kernel class (SURVEY.md section 8d formulas)."""
     from pcrcg_b200 import blocks
     N = [int(p.shape[0]) for p in batch["points"]]
@@ -202,6 +242,10 @@ def algorithmic_work(batch, cfg, limits, enc):
                 if isinstance(u, blocks.UnaryBlock):
                     lin_f += 2 * rows * u.in_dim * u.out_dim
                     lin_b += 4 * (rows * u.in_dim + u.in_dim * u.out_dim + rows * u.out_dim)
+    if views is not None:        # projection-scatter: 12 N + 4 HW per view + 4 M C (gathered) + 4 N (C+1); M <= N (every point seen)
+        nv = sum(len(v) for v in views)
+        C2, Hh, Ww = views[0][0]["feature2d"].shape
+        work["projection"] = dict(bytes=12 * N[0] + 4 * Hh * Ww * nv + 4 * N[0] * C2 + 4 * N[0] * (C2 + 1), flops=0)
     work["kpconv_aggregate"] = dict(bytes=agg_b, flops=agg_f)
     work["gemm"] = dict(bytes=gemm_b + lin_b, flops=gemm_f + lin_f, kpconv_flops=gemm_f, linear_flops=lin_f)
     return work, N
@@ -213,7 +257,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="3dmatch", choices=["3dmatch", "3dlomatch", "kitti"])
+    ap.add_argument("--workload", default="3dmatch", choices=["3dmatch", "3dlomatch", "kitti", "colour"])
     ap.add_argument("--pairs", type=int, default=32, help="fragment pairs per step per GPU")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -238,7 +282,9 @@ def main():
     cfg, limits = workload_config(args.workload)
     wl_name = {"3dmatch": "configs[1]: 3DMatch-shaped synthetic pair batch (~20k pts/fragment, calibrated limits)",
                "3dlomatch": "configs[2]: 3DLoMatch-shaped synthetic low-overlap pairs",
-               "kitti": "configs[3]: KITTI-shaped synthetic scans (voxel 0.3, 4-layer KPConv)"}[args.workload]
+               "kitti": "configs[3]: KITTI-shaped synthetic scans (voxel 0.3, 4-layer KPConv)",
+               "colour": "configs[4]: PCR-CG colour path: 2D feature un-projection (2 views per cloud, 128-channel maps) + KPConv "
+                         "encoder with in_feats_dim = 129 on 3DMatch-shaped RGB-D synthetic data"}[args.workload]
 
     # random-init weights of the named architecture, identical on every rank and for both arms
     torch.manual_seed(0)
@@ -254,12 +300,13 @@ def main():
         # reference's DataLoader workers), then the encoder runs pair by pair on all host threads
         PS = max(1, min(8, threads // 2))
         samples = [make_pairs(args.workload, PS, 10_000 + PS * k) for k in range(max(1, min(K, 3)))]      # generated outside the clock
+        sviews = [make_views_np(sm, 10_000 + PS * k) if args.workload == "colour" else None for k, sm in enumerate(samples)]
         for _ in range(W):
-            cpu_reference_run(samples[0], cfg, limits, state_dict, threads)
+            cpu_reference_run(samples[0], cfg, limits, state_dict, threads, sviews[0])
         t0 = time.perf_counter()
         detail = None
         for k in range(K):
-            _, kind, detail = cpu_reference_run(samples[k % len(samples)], cfg, limits, state_dict, threads)
+            _, kind, detail = cpu_reference_run(samples[k % len(samples)], cfg, limits, state_dict, threads, sviews[k % len(samples)])
         dt = time.perf_counter() - t0
         v = PS * K / dt
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
@@ -278,7 +325,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (the preprocessing workers are forked)
         sample = make_pairs(args.workload, args.cpu_sample_pairs, 20_000)
-        v, kind, detail = cpu_reference_run(sample, cfg, limits, state_dict, threads)
+        v, kind, detail = cpu_reference_run(sample, cfg, limits, state_dict, threads,
+                                            make_views_np(sample, 20_000) if args.workload == "colour" else None)
         cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                     "sample": f"{len(sample)} synthetic pairs of the same workload: reference C++ subsample/search in {detail['workers']} worker "
                               f"processes + PyTorch-CPU encoder on {threads} threads", "detail": detail}
@@ -319,6 +367,10 @@ def main():
     lens_host = torch.from_numpy(lens_np).pin_memory()
     path = pipeline.FeaturePath(cfg, limits, device=dev, state_dict=state_dict)
     pts_dev, lens_dev = pts_host.to(dev), lens_host.to(dev)
+    views_np = make_views_np(pairs, rank * P) if args.workload == "colour" else None
+    views_dev = views_to_device(views_np, dev) if views_np is not None else None
+    views_e2e = views_to_device(views_np, dev, depth_on_host=True) if views_np is not None else None
+    depth_bytes = sum(v["depth"].numel() * 4 for vs in (views_e2e or []) for v in vs)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -328,11 +380,11 @@ def main():
 
     y = None
     for _ in range(W):
-        y, batch = path.run_device(pts_dev, lens_dev)
+        y, batch = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
     out_bufs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
     for i in range(2):
-        path.run_host(pts_host, lens_host, out_bufs[i])
-    work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder)
+        path.run_host(pts_host, lens_host, out_bufs[i], views_e2e)
+    work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder, views_dev)
 
     # ---- parity of THIS batch, outside every timed region: one pair of the stacked run vs the reference run on that pair
     # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
@@ -343,9 +395,17 @@ def main():
         cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
         n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
         seg = batch["pair_segments"][-1].cpu().tolist()
-        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg)
+        x_cpu, x_equal = None, None
+        if views_np is not None:                          # colour: the un-projected input rows of the pair, bit for bit
+            from pcrcg_b200 import projection
+            x_cpu = cpu_unproject(pairs[kq], views_np[2 * kq:2 * kq + 2])
+            x_dev = projection.unproject_features_batch(pts_dev, lens_dev, views_dev)
+            st0 = int(batch["pair_segments"][0][kq].item())
+            x_equal = bool(np.array_equal(x_dev[st0:st0 + x_cpu.shape[0]].cpu().numpy(), x_cpu))
+        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg, x=x_cpu)
         parity = {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
-                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "ok": (not bad) and enc_err < 1e-3,
+                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "unprojected_rows_equal": x_equal,
+                  "ok": (not bad) and enc_err < 1e-3 and x_equal is not False,
                   "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
 
     # ---- device-resident timed region ----------------------------------------------------------
@@ -359,7 +419,7 @@ def main():
     e0.record()
     for _ in range(K):
         flush.fill_(0.0)                                  # L2 flush between timed iterations
-        y, _ = path.run_device(pts_dev, lens_dev)
+        y, _ = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -370,7 +430,7 @@ def main():
     barrier()
     for _ in range(K):
         flush.fill_(0.0)
-        path.run_device(pts_dev, lens_dev)
+        path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
     barrier()
     ncls = L.pcrcg_profile_classes()
     ms_arr, cnt_arr = (C.c_double * ncls)(), (C.c_int64 * ncls)()
@@ -389,7 +449,7 @@ def main():
         if pending[i & 1] is not None:
             pending[i & 1].result()
         flush.fill_(0.0)
-        pending[i & 1] = path.submit_host(pts_host, lens_host, out_bufs[i & 1])
+        pending[i & 1] = path.submit_host(pts_host, lens_host, out_bufs[i & 1], views_e2e)
     for h in pending:
         if h is not None:
             out, _ = h.result()
@@ -415,7 +475,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         kernels = {}
         agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
-               "kpconv_fused": ["kpconv_fused"], "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"]}
+               "kpconv_fused": ["kpconv_fused"], "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"], "projection": ["projection"]}
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, parts in agg.items():
             ms = sum(prof[p][0] for p in parts if p in prof) / K
@@ -449,7 +509,7 @@ def main():
                            "(fp32 CUDA cores for ragged shapes such as Cin=1)",
                            "parallelism": f"pairs sharded by rank x{world}, no collective on the path"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes + lens_np.nbytes),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pts_np.nbytes + lens_np.nbytes + depth_bytes),
                         "d2h_bytes_per_step": int(out.numel() * 4 + lens_np.nbytes), "ms_per_step": e2e_ms / K},
                 "gpu_launches": launches, "roofline": roof, "kernels": kernels}
         if cpu_base is not None:

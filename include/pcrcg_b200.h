@@ -241,6 +241,13 @@ int pcrcg_project_scatter_dev(const float* points, int64_t n, int32_t nviews, co
                               const float* const* valid, const float* w2c, const float* k4, const int32_t* row_lo,
                               const int32_t* row_hi, int32_t H, int32_t W, int32_t C, float thresh, const float* base, float* out,
                               pcrcg_stream_t stream);
+/* The same for a stacked batch (any number of clouds and views): everything in DEVICE memory.  cloud_starts [nb+1] = row
+ * starts of the clouds; the views of cloud c are views[view_starts[c] .. view_starts[c+1]) in write order; one view is
+ * { const float* depth; const float* feat; const float* valid; float w2c[12]; float k4[12]; } (rows 0-2 of the 4x4
+ * matrices, row-major; 120 bytes, 8-byte aligned). */
+int pcrcg_project_scatter_batch_dev(const float* points, int64_t n, const int32_t* cloud_starts, int32_t nb,
+                                    const int32_t* view_starts, const void* views, int32_t H, int32_t W, int32_t C, float thresh,
+                                    const float* base, float* out, pcrcg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -83,8 +83,9 @@ def compare_pair(batch, k, cpu):
     return n, bad
 
 
-def encoder_error(y_pair, cpu, state_dict, cfg):
-    """y_pair: the GPU encoder's rows of one pair (coarsest level) -> normwise max error vs blocks_port on that pair"""
+def encoder_error(y_pair, cpu, state_dict, cfg, x=None):
+    """y_pair: the GPU encoder's rows of one pair (coarsest level) -> normwise max error vs blocks_port on that pair.
+    x: the pair's input feature rows (default: ones [N, in_feats_dim], the reference's geometry-only input)"""
     import torch
     from oracle import blocks_port as bp
     desc = bp.encoder_blocks_from_state_dict({k: v.cpu() for k, v in state_dict.items()}, prefix="encoder_blocks.",
@@ -92,6 +93,7 @@ def encoder_error(y_pair, cpu, state_dict, cfg):
                                              KP_extent=cfg.KP_extent)
     b = {k: [torch.from_numpy(np.ascontiguousarray(a)) for a in cpu[k]] for k in ("points", "neighbors", "pools", "upsamples")}
     with torch.no_grad():
-        ref, _ = bp.encoder(torch.ones(b["points"][0].shape[0], cfg.in_feats_dim), b, desc)
+        x0 = torch.ones(b["points"][0].shape[0], cfg.in_feats_dim) if x is None else torch.as_tensor(x)
+        ref, _ = bp.encoder(x0, b, desc)
     y = y_pair.detach().cpu()
     return float((y - ref).abs().max() / ref.abs().max())

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pcrcg_projection_ws_bytes": (_SZ, [_I64]),
     "pcrcg_projection_dev": (C.c_int, [_P, _I64, _P, _I32, _I32, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
     "pcrcg_project_scatter_dev": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
+    "pcrcg_project_scatter_batch_dev": (C.c_int, [_P, _I64, _P, _I32, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
     "pcrcg_knn_dev": (C.c_int, [_P, _I64, _P, _I32, _I32, _P, _P]),
     "pcrcg_edge_max_stats_dev": (C.c_int, [_P, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P]),
     "pcrcg_bias_act_dev": (C.c_int, [_P, _I64, _I32, _P, _F, _P, _P]),

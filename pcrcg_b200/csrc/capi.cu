@@ -97,6 +97,8 @@ int mutual_dev(const int32_t*, const int32_t*, int64_t, uint8_t*, cudaStream_t);
 size_t projection_ws_bytes(int64_t n);
 int projection_dev(const float*, int64_t, const float*, int32_t, int32_t, const float*, const float*, float, long long*, long long*, int32_t*,
                    void*, size_t, cudaStream_t);
+int project_scatter_batch_dev(const float*, int64_t, const int32_t*, int32_t, const int32_t*, const void*, int32_t, int32_t, int32_t, float, const float*,
+                              float*, cudaStream_t);
 int project_scatter_dev(const float*, int64_t, int32_t, const float* const*, const float* const*, const float* const*, const float*,
                         const float*, const int32_t*, const int32_t*, int32_t, int32_t, int32_t, float, const float*, float*, cudaStream_t);
 
@@ -418,6 +420,13 @@ int pcrcg_project_scatter_dev(const float* points, int64_t n, int32_t nviews, co
 {
     return project_scatter_dev(points, n, nviews, depth, feat, valid, w2c, k4, row_lo, row_hi, H, W, C, thresh, base, out,
                                (cudaStream_t)stream);
+}
+
+int pcrcg_project_scatter_batch_dev(const float* points, int64_t n, const int32_t* cloud_starts, int32_t nb, const int32_t* view_starts,
+                                    const void* views, int32_t H, int32_t W, int32_t C, float thresh, const float* base, float* out,
+                                    pcrcg_stream_t stream)
+{
+    return project_scatter_batch_dev(points, n, cloud_starts, nb, view_starts, views, H, W, C, thresh, base, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1059,6 +1059,38 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
     }
 }
 
+// cin = 64 m + 1 (PCR-CG's colour input: 128 image-feature channels + 1, configs/test/indoor.yaml:34): the first 64 m channels
+// take the bf16 plane kernels, the last one the one-thread-per-(point, kernel point) kernel, and the aggregate's K axis is
+// laid out as [kp][64 m channels, kperm64 inside each slab] followed by [kp] for the odd channel.  This kernel splits the
+// weights [K, cin, cout] into bf16 hi/lo [cout, ldk] with the same K order.
+__global__ void __launch_bounds__(256) k_split_w_tail1(const float* __restrict__ w, int K, int cin, int cout, __nv_bfloat16* __restrict__ hi,
+                                                       __nv_bfloat16* __restrict__ lo, int ldk)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)K * cin * cout) return;
+    const int n = (int)(e % cout);
+    const int kc = (int)(e / cout), k = kc / cin, c = kc - k * cin;
+    const int cm = cin - 1;
+    const int dst = c < cm ? k * cm + ((c & ~63) | kperm64(c & 63)) : K * cm + k;
+    const float v = w[e];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[(size_t)n * ldk + dst] = h;
+    lo[(size_t)n * ldk + dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// planes of the first `cols` channels of fp32 rows (pitch ldx) -- hi = bf16(x), lo = bf16(x - hi)
+__global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ x, int ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                                    __nv_bfloat16* __restrict__ lo)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * cols) return;
+    const int r = (int)(e / cols), c = (int)(e - (long long)r * cols);
+    const float v = x[(size_t)r * ldx + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // first_layer_fused: measured on B200 at 1.33 ms per 32-pair step against 0.88 + 0.31 ms for aggregate_small + the CUDA-core
 // contraction (one short-lived block per 32 points: latency-bound behind its staging barrier) -> opt-in until it is persistent
 static int g_agg_simt = 0, g_agg_pipelined = 1, g_small_fused = 0;
@@ -1155,8 +1187,9 @@ size_t kpconv_ws_bytes(int64_t nq, int64_t ns, int32_t cin, int32_t K)
     size_t ldk = ((size_t)K * cin + 7) / 8 * 8;
     size_t chunk = (size_t)kpconv_chunk_rows(nq, ldk);
     const size_t nbuf = (int64_t)chunk < nq ? 2 : 1;          // the second (alternating) buffer only exists when the rows are chunked
+    const size_t tail_planes = (cin > 64 && cin % 64 == 1) ? align_up((size_t)ns * (cin - 1) * 4, 256) : 0;      // hi + lo planes of 64 m channels
     return nbuf * align_up(chunk * ldk * sizeof(float), 256) + align_up((size_t)nq * sizeof(float), 256) + align_up((size_t)ns, 256) +
-           align_up((size_t)2048 * ldk * sizeof(float), 256) + 2048;      // + split weights for cout <= 2048
+           align_up((size_t)2048 * ldk * sizeof(float), 256) + tail_planes + 2048;      // + split weights for cout <= 2048
 }
 
 // weights: [K, cin, cout] row-major (the reference's Parameter layout)
@@ -1190,6 +1223,12 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     const uint8_t* rowflag = rowflag_in != nullptr ? rowflag_in : rowflag_ws;
     __nv_bfloat16* b_hi = (__nv_bfloat16*)W.take<float>((size_t)cout * ldk);
     __nv_bfloat16* b_lo = b_hi + (size_t)cout * ldk;
+    // cin = 64 m + 1 on the tensor path: planes of the first 64 m channels are made here (see k_split_w_tail1)
+    const bool tail1 = !gemm_force_simt_get() && gemm_tc_shape_ok((int)nq, cout, KC) && x != nullptr && x_hi == nullptr && cin > 64 &&
+                       cin % 64 == 1 && H <= 64 && !g_agg_simt && ns > 0 && g_agg_pipelined;
+    const int cin_m = cin - 1;
+    __nv_bfloat16* t_hi = tail1 ? (__nv_bfloat16*)W.take<float>((size_t)ns * cin_m) : nullptr;
+    __nv_bfloat16* t_lo = tail1 ? t_hi + (size_t)ns * cin_m : nullptr;
     PCRCG_REQUIRE(ws != nullptr && W.ok(), "kpconv: workspace too small (%zu < %zu)", ws_bytes, W.off);
     const float inv_extent = 1.0f / kp_extent;
     if (ns > 0 && rowflag_in == nullptr) {
@@ -1203,7 +1242,12 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     const bool pipelined = planes && g_agg_pipelined && H <= 64;
     const bool fused = pipelined && g_fused > 0 && kpconv_fused_shape_ok(nq, ns, H, cin, cout, K, ldxs) &&
                        (g_fused > 1 || (cin == 64 && cout == 64));
-    if (tc) {
+    if (tail1) {
+        ProfScope prof(PC_KPCONV_AGG, st, 2);
+        k_split_rows<<<(unsigned)cdiv64((int64_t)ns * cin_m, 256), 256, 0, st>>>(x, cin, (int)ns, cin_m, t_hi, t_lo);
+        k_split_w_tail1<<<(unsigned)cdiv64((int64_t)K * cin * cout, 256), 256, 0, st>>>(weights, K, cin, cout, b_hi, b_lo, ldk);
+        PCRCG_CUDA(cudaGetLastError());
+    } else if (tc) {
         ProfScope prof(fused ? PC_KPCONV_FUSED : PC_GEMM, st, 0);
         PCRCG_TRY(gemm_tc_split_b_perm_dev(weights, cout, 0, cout, KC, ldk, b_hi, b_lo, pipelined ? 1 : 0, st));
     }
@@ -1236,7 +1280,28 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
         {
             ProfScope prof(PC_KPCONV_AGG, st, 1);
             int rc;
-            if (pipelined) {
+            if (tail1) {
+                // channels [0, 64 m): persistent plane kernel into K columns [kp][64 m]; channel 64 m: K columns K * 64 m + kp
+                const unsigned gy = (unsigned)(cin_m / 64);
+                unsigned gx = (unsigned)cdiv64(kNumSMs * 5, gy);
+                if ((int64_t)gx > cdiv64(rows, AB_WARPS)) gx = (unsigned)cdiv64(rows, AB_WARPS);
+                const dim3 grid(gx, gy);
+                __nv_bfloat16* th = wf_hi + (size_t)K * cin_m;
+                __nv_bfloat16* tl = wf_lo + (size_t)K * cin_m;
+                if (idx_is_i64) {
+                    k_kpconv_aggregate_bf16p<long long><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
+                        t_hi, t_lo, cin_m, cin_m, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                    k_kpconv_aggregate_small<long long, 1, true><<<(unsigned)cdiv64(rows, 16), 256, 0, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H,
+                        idx_stride, x + cin_m, cin, rowflag, kpts, K, inv_extent, nullptr, th, tl, ldk, inv_cnt + r0);
+                } else {
+                    k_kpconv_aggregate_bf16p<int><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
+                        t_hi, t_lo, cin_m, cin_m, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                    k_kpconv_aggregate_small<int, 1, true><<<(unsigned)cdiv64(rows, 16), 256, 0, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H,
+                        idx_stride, x + cin_m, cin, rowflag, kpts, K, inv_extent, nullptr, th, tl, ldk, inv_cnt + r0);
+                }
+                rc = cudaGetLastError() == cudaSuccess ? PCRCG_OK : PCRCG_ERR;
+                if (rc) set_error("kpconv: (64 m + 1)-channel aggregate launch failed");
+            } else if (pipelined) {
                 // persistent: ~5 resident CTAs per SM in total, each warp walks over points with a fixed stride
                 const unsigned gy = (unsigned)(cin / 64);
                 unsigned gx = (unsigned)cdiv64(kNumSMs * 5, gy);

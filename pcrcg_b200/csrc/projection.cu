@@ -102,6 +102,56 @@ __global__ void __launch_bounds__(256) k_project_scatter(const float* __restrict
     if (lane == 0) o[C] = 1.0f;
 }
 
+// Any number of clouds and views (a stacked batch of fragment pairs): the views live in DEVICE memory, grouped by cloud in
+// the reference's write order (views [view_starts[c], view_starts[c+1]) belong to cloud c = rows [cloud_starts[c],
+// cloud_starts[c+1])); as above the last view of its cloud that sees a point wins.
+struct ViewDev {
+    const float* depth;   // [H,W]
+    const float* feat;    // [C,H,W]
+    const float* valid;   // [H,W] or nullptr
+    Mat34 w2c, k4;
+};
+
+__global__ void __launch_bounds__(256) k_project_scatter_batch(const float* __restrict__ pts, int n, const int32_t* __restrict__ cloud_starts, int nb,
+                                                               const int32_t* __restrict__ view_starts, const ViewDev* __restrict__ views, int H,
+                                                               int W, int C, float thresh, const float* __restrict__ base, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+    const int c = cloud_of(cloud_starts, nb, i);
+    int win = -1, px = 0, py = 0;
+    for (int v = view_starts[c + 1] - 1; v >= view_starts[c]; v--) {
+        if (project_point(views[v].w2c, views[v].k4, x, y, z, views[v].depth, H, W, thresh, px, py)) { win = v; break; }
+    }
+    float* o = out + (size_t)i * (C + 1);
+    if (win < 0) {
+        const float b = base ? base[i] : 1.0f;
+        for (int ch = lane; ch <= C; ch += 32) o[ch] = b;
+        return;
+    }
+    const float* f = views[win].feat + (size_t)py * W + px;
+    const float* vmp = views[win].valid;
+    const float vm = vmp ? vmp[(size_t)py * W + px] : 1.0f;
+    const size_t plane = (size_t)H * W;
+    for (int ch = lane; ch < C; ch += 32) o[ch] = vmp ? __fmul_rn(f[ch * plane], vm) : f[ch * plane];
+    if (lane == 0) o[C] = 1.0f;
+}
+
+int project_scatter_batch_dev(const float* pts, int64_t n, const int32_t* cloud_starts, int32_t nb, const int32_t* view_starts,
+                              const void* views, int32_t H, int32_t W, int32_t C, float thresh, const float* base, float* out, cudaStream_t st)
+{
+    PCRCG_REQUIRE(n >= 0 && n < (1ll << 30) && nb >= 1 && H >= 1 && W >= 1 && C >= 1, "project_scatter: bad dimensions");
+    PCRCG_REQUIRE(cloud_starts != nullptr && view_starts != nullptr && views != nullptr, "project_scatter: null argument");
+    if (n == 0) return PCRCG_OK;
+    ProfScope prof(PC_PROJECT, st, 1);
+    k_project_scatter_batch<<<(unsigned)cdiv64(n, 8), 256, 0, st>>>(pts, (int)n, cloud_starts, nb, view_starts, (const ViewDev*)views, H, W, C, thresh,
+                                                                    base, out);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
 size_t projection_ws_bytes(int64_t n) { return align_up((size_t)(n + 1) * 4, 256) * 2 + scan_ws_bytes(n) + 1024; }
 
 static void to34(const float* m16, Mat34& o) { for (int k = 0; k < 12; k++) o.m[k] = m16[k]; }

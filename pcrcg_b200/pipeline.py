@@ -51,22 +51,27 @@ class FeaturePath:
         self.encoder.to(self.device).eval()
 
     @torch.no_grad()
-    def run_device(self, points, lengths, features=None):
-        """points [N,3] f32 cuda, lengths [2P] i32 cuda -> (features of the coarsest level [N3, C], batch dict)"""
+    def run_device(self, points, lengths, features=None, views_per_cloud=None):
+        """points [N,3] f32 cuda, lengths [2P] i32 cuda -> (features of the coarsest level [N3, C], batch dict).
+        views_per_cloud (colour path, in_feats_dim = C2d + 1): per cloud its RGB-D views in write order (see
+        projection.unproject_features_batch); the 2D features are un-projected onto the points and form the input rows."""
+        if views_per_cloud is not None:
+            from . import projection
+            features = projection.unproject_features_batch(points, lengths, views_per_cloud)
         batch = dataloader.build_pyramid(points, lengths, self.config, self.limits, device=self.device)
         if features is None:
             features = torch.ones((points.shape[0], self.config.in_feats_dim), dtype=torch.float32, device=self.device)
         return self.encoder(features, batch), batch
 
     @torch.no_grad()
-    def run_host(self, points_host, lengths_host, out_host=None):
+    def run_host(self, points_host, lengths_host, out_host=None, views_per_cloud=None):
         """HOST buffers in and out.  points_host [N,3] f32 (pinned for async copies), lengths_host [2P] i32.
         Returns (features_host [N3,C], lengths of the coarsest level [2P] on the host)."""
-        h = self.submit_host(points_host, lengths_host, out_host)
+        h = self.submit_host(points_host, lengths_host, out_host, views_per_cloud)
         return h.result()
 
     @torch.no_grad()
-    def submit_host(self, points_host, lengths_host, out_host=None):
+    def submit_host(self, points_host, lengths_host, out_host=None, views_per_cloud=None):
         """Pipelined form of :meth:`run_host`: the device->host copy of the result runs on a separate copy
         stream, so it overlaps the next submission's compute.  Returns a handle; ``handle.result()`` waits for
         this submission only.  ``out_host`` (pinned, reused by the caller once result() returned) avoids a
@@ -76,7 +81,7 @@ class FeaturePath:
             self._pinned_small, self._slot = {}, 0
         pts = points_host.to(self.device, non_blocking=True)
         lens = lengths_host.to(self.device, non_blocking=True)
-        y, batch = self.run_device(pts, lens)
+        y, batch = self.run_device(pts, lens, views_per_cloud=views_per_cloud)
         coarse_dev = batch["stack_lengths"][-1]
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))

@@ -110,3 +110,61 @@ def unproject_features(points, views, base=None, thresh=0.1):
                                               hi.ctypes.data, H, W, Cc, float(thresh), b.data_ptr() if b is not None else None,
                                               out.data_ptr(), _stream()))
     return out
+
+
+VIEW_DTYPE = np.dtype([("depth", np.uint64), ("feat", np.uint64), ("valid", np.uint64), ("w2c", np.float32, 12), ("k4", np.float32, 12)])
+
+
+def unproject_features_batch(points, lengths, views_per_cloud, base=None, thresh=0.1):
+    """:func:`unproject_features` for a STACKED batch: points [N,3] cuda = clouds of ``lengths`` [B] rows each;
+    ``views_per_cloud[c]`` = the views of cloud c in the reference's write order (image 2, then image 1:
+    models/architectures.py:367-370), dicts as in :func:`unproject_features` (``rows`` is implied by the cloud).  One launch for
+    any number of clouds and views.  Returns x [N, C+1]."""
+    pts = _f32c(points)
+    dev = pts.device
+    n = pts.shape[0]
+    lens = np.asarray(torch.as_tensor(lengths).cpu(), dtype=np.int64).reshape(-1)
+    nb = len(lens)
+    if len(views_per_cloud) != nb or int(lens.sum()) != n:
+        raise RuntimeError("unproject_features_batch: one view list per cloud, lengths summing to the number of points")
+    cloud_starts = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    view_starts = np.concatenate([[0], np.cumsum([len(v) for v in views_per_cloud])]).astype(np.int32)
+    nv = int(view_starts[-1])
+    if nv == 0:
+        raise RuntimeError("unproject_features_batch: no views")
+    rec = np.zeros(nv, VIEW_DTYPE)
+    keep, Cc, H, W, k = [], None, None, None, 0
+    for c, vlist in enumerate(views_per_cloud):
+        for view in vlist:
+            d = _f32c(torch.as_tensor(view["depth"]).to(dev))
+            d = d.reshape(d.shape[-2], d.shape[-1])
+            f = _f32c(torch.as_tensor(view["feature2d"]).to(dev))
+            if f.dim() != 3:
+                raise RuntimeError(f"unproject_features_batch: cloud {c}: feature2d must be [C,H,W], got {tuple(f.shape)}")
+            if Cc is None:
+                Cc, H, W = f.shape
+            if tuple(f.shape) != (Cc, H, W) or tuple(d.shape) != (H, W):
+                raise RuntimeError(f"unproject_features_batch: cloud {c}: feature2d {tuple(f.shape)} / depth {tuple(d.shape)} differ from "
+                                   f"the first view's (C, H, W) = {(Cc, H, W)}")
+            vm = view.get("valid_map")
+            if vm is not None:
+                vm = torch.as_tensor(vm).to(dev)
+                vm = vm.reshape(vm.shape[-2], vm.shape[-1])
+                if tuple(vm.shape) == (W, H) and H != W:
+                    vm = vm.t()
+                if tuple(vm.shape) != (H, W):
+                    raise RuntimeError(f"unproject_features_batch: cloud {c}: valid_map {tuple(vm.shape)} is neither (H, W) nor (W, H)")
+                vm = _f32c(vm)
+            keep += [d, f, vm]
+            rec[k]["depth"], rec[k]["feat"], rec[k]["valid"] = d.data_ptr(), f.data_ptr(), (vm.data_ptr() if vm is not None else 0)
+            rec[k]["w2c"], rec[k]["k4"] = _mat16(view["world2camera"])[:12], _mat16(view["intrinsics"])[:12]
+            k += 1
+    out = torch.empty((n, Cc + 1), dtype=torch.float32, device=dev)
+    b = _f32c(base.reshape(-1)) if base is not None else None
+    cs = torch.from_numpy(cloud_starts).to(dev)
+    vs = torch.from_numpy(view_starts).to(dev)
+    vd = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(dev)
+    with torch.cuda.device(dev):
+        check(lib().pcrcg_project_scatter_batch_dev(pts.data_ptr(), n, cs.data_ptr(), nb, vs.data_ptr(), vd.data_ptr(), H, W, Cc, float(thresh),
+                                                    b.data_ptr() if b is not None else None, out.data_ptr(), _stream()))
+    return out

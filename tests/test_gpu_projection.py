@@ -98,3 +98,29 @@ def test_unproject_validates_views_and_accepts_reference_valid_map_layout():
         gp.unproject_features(pts, [mk(vs[0])] * 9)
     with pytest.raises(RuntimeError, match="rows"):
         gp.unproject_features(pts, [mk(vs[0], rows=(0, len(src) + 1))])
+
+
+def test_unproject_batch_equals_per_pair_calls_and_oracle():
+    """one launch for a stacked batch (3 pairs, 12 views, device-resident view table) == the per-pair 8-view entry point ==
+    the oracle's scatter, bit for bit"""
+    pairs = [synthetic.match3d_pair(20 + k, n_target=2500 + 300 * k)[:2] for k in range(3)]
+    clouds = [c for p in pairs for c in p]
+    pts = torch.from_numpy(np.concatenate(clouds)).to(DEV)
+    lens = np.array([len(c) for c in clouds], np.int32)
+    per_cloud, oracle_rows, lo = [], [], 0
+    for ci, cloud in enumerate(clouds):
+        vs = synthetic.rgbd_views(cloud, 40 + ci, n_views=2, channels=24)[::-1]
+        per_cloud.append([dict(v, feature2d=torch.from_numpy(v["feature2d"]).to(DEV)) for v in vs])
+        ov = []
+        for v in vs:
+            i2, i3 = pp.projection(cloud, v["depth"], v["world2camera"], v["intrinsics"])
+            ov.append((v["feature2d"], v["valid_map"], i2, i3))
+        oracle_rows.append(pp.scatter_image_features(len(cloud), ov))
+        lo += len(cloud)
+    x = gp.unproject_features_batch(pts, lens, per_cloud)
+    assert np.array_equal(x.cpu().numpy(), np.concatenate(oracle_rows))
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    for k in range(3):                                                    # the 8-view entry point, pair by pair
+        a, b, c = int(starts[2 * k]), int(starts[2 * k + 1]), int(starts[2 * k + 2])
+        views = [dict(v, rows=(0, b - a)) for v in per_cloud[2 * k]] + [dict(v, rows=(b - a, c - a)) for v in per_cloud[2 * k + 1]]
+        assert torch.equal(gp.unproject_features(pts[a:c], views), x[a:c])
