@@ -251,6 +251,62 @@ def algorithmic_work(batch, cfg, limits, enc, views=None):
     return work, N
 
 
+def quick_measure(workload, P, K, W, rank, world, dev, flush, dist):
+    """A short device-timed + end-to-end measurement of ANOTHER workload of BASELINE.json (configs[2..4]) inside the same run,
+    same rules as the main line (L2 flush between iterations, CUDA events, barrier + max over ranks), so that every config is
+    visible wherever the default line is (1 GPU and the 1/2/4/8-GPU scaling runs)."""
+    import torch
+    from pcrcg_b200 import pipeline
+    cfg, limits = workload_config(workload)
+    pairs = make_pairs(workload, P, rank * P)
+    pts_np, lens_np = pipeline.stack_pairs(pairs)
+    pts_host, lens_host = torch.from_numpy(pts_np).pin_memory(), torch.from_numpy(lens_np).pin_memory()
+    pts_dev, lens_dev = pts_host.to(dev), lens_host.to(dev)
+    views_np = make_views_np(pairs, rank * P) if workload == "colour" else None
+    views_dev = views_to_device(views_np, dev) if views_np is not None else None
+    views_e2e = views_to_device(views_np, dev, depth_on_host=True) if views_np is not None else None
+    path = pipeline.FeaturePath(cfg, limits, device=dev, seed=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        y, batch = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
+    outs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
+    path.run_host(pts_host, lens_host, outs[0], views_e2e)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        flush.fill_(0.0)
+        y, _ = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    pending = [None, None]
+    for i in range(K):
+        if pending[i & 1] is not None:
+            pending[i & 1].result()
+        flush.fill_(0.0)
+        pending[i & 1] = path.submit_host(pts_host, lens_host, outs[i & 1], views_e2e)
+    for h in pending:
+        if h is not None:
+            h.result()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    del path, outs, views_dev, views_e2e
+    torch.cuda.empty_cache()
+    return {"workload": workload, "pairs_per_step_per_gpu": P, "steps": K, "warmup": W, "value": world * P * K / (ms / 1000.0), "unit": UNIT,
+            "ms_per_step": ms / K, "e2e_value": world * P * K / (e2e_ms / 1000.0), "points_per_level": [int(p.shape[0]) for p in batch["points"]],
+            "limits": list(limits), "list_widths": [int(t.shape[1]) for t in batch["neighbors"]]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,6 +318,9 @@ def main():
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--extra-workloads", default="3dlomatch:32,kitti:16,colour:16",
+                    help="other BASELINE.json configs measured briefly in the same run (workload:pairs,...; '' = none); only with the "
+                         "default workload")
     ap.add_argument("--parity-pair", type=int, default=0, help="pair of the batch checked against the oracle (outside the timed regions)")
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core contraction")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
@@ -465,6 +524,12 @@ def main():
     value = world * P * K / (ms_total / 1000.0)
     e2e_value = world * P * K / (e2e_ms / 1000.0)
 
+    extras = []
+    if args.workload == "3dmatch" and args.extra_workloads:
+        for item in args.extra_workloads.split(","):
+            wl, _, pp_ = item.partition(":")
+            extras.append(quick_measure(wl, int(pp_ or 16), max(3, min(K, 5)), 3, rank, world, dev, flush, dist if world > 1 else None))
+
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -516,6 +581,8 @@ def main():
             line["cpu_baseline"] = cpu_base
         if parity is not None:
             line["parity_check"] = parity
+        if extras:
+            line["other_workloads"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

