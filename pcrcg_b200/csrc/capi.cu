@@ -51,6 +51,7 @@ int subsample_batch_dev(const float*, int64_t, const int32_t*, int32_t, float, i
 size_t radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
 int radius_build_dev(const float*, int64_t, const int32_t*, int32_t, float, void*, size_t, cudaStream_t);
 size_t radius_query_ws_bytes(int64_t nq, int32_t nb);
+bool radius_cells_preferred(int32_t width);
 int radius_query_cells_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, float, int32_t, int32_t, int32_t*, int32_t*, int32_t*,
                            void*, size_t, void*, size_t, int32_t, cudaStream_t);
 int radius_query_dev(const float*, int64_t, const int32_t*, int64_t, int32_t, float, int32_t, int32_t, int32_t*, int32_t*, int32_t*,
@@ -202,6 +203,9 @@ int pcrcg_radius_query_cells_dev(const float* queries, int64_t nq, const int32_t
                                  int32_t width, int32_t row_stride, int32_t* rows, int32_t* counts, int32_t* max_count, void* ws,
                                  size_t ws_bytes, void* qws, size_t qws_bytes, int32_t queries_are_supports, pcrcg_stream_t stream)
 {
+    if (!radius_cells_preferred(width))          // wide lists / count-only passes: one warp per query (see radius.cu)
+        return radius_query_dev(queries, nq, q_lens, ns, nb, radius, width, row_stride, rows, counts, max_count, ws, ws_bytes,
+                                (cudaStream_t)stream);
     return radius_query_cells_dev(queries, nq, q_lens, ns, nb, radius, width, row_stride, rows, counts, max_count, ws, ws_bytes, qws,
                                   qws_bytes, queries_are_supports, (cudaStream_t)stream);
 }
@@ -226,15 +230,15 @@ int pcrcg_batch_query_host(const float* queries, int64_t nq, const float* suppor
     PCRCG_CUDA(cudaMemcpy(dql.p, q_lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
     PCRCG_CUDA(cudaMemcpy(dsl.p, s_lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
     PCRCG_TRY(radius_build_dev(ds.as<float>(), ns, dsl.as<int32_t>(), nb, radius, dws.p, wsb, 0));
-    PCRCG_TRY(radius_query_cells_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, 0, 0, nullptr, nullptr, dmax.as<int32_t>(),
-                                     dws.p, wsb, dqws.p, qwsb, 0, 0));
+    PCRCG_TRY(radius_query_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, 0, 0, nullptr, nullptr, dmax.as<int32_t>(),
+                               dws.p, wsb, 0));
     int32_t mx = 0;
     PCRCG_CUDA(cudaMemcpy(&mx, dmax.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
     PCRCG_REQUIRE(mx >= 1, "Error");      // cpp_neighbors/wrapper.cpp:201-205
     int32_t width = (limit > 0 && limit < mx) ? limit : mx;
     PCRCG_TRY(drows.alloc(sizeof(int32_t) * (size_t)nq * width));
-    PCRCG_TRY(radius_query_cells_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, width, width, drows.as<int32_t>(), nullptr,
-                                     nullptr, dws.p, wsb, dqws.p, qwsb, 0, 0));
+    PCRCG_TRY(pcrcg_radius_query_cells_dev(dq.as<float>(), nq, dql.as<int32_t>(), ns, nb, radius, width, width, drows.as<int32_t>(), nullptr,
+                                           nullptr, dws.p, wsb, dqws.p, qwsb, 0, 0));
     int32_t* o = (int32_t*)malloc(sizeof(int32_t) * (size_t)nq * width);
     PCRCG_REQUIRE(o != nullptr, "batch_query: out of host memory");
     cudaError_t e = cudaMemcpy(o, drows.p, sizeof(int32_t) * (size_t)nq * width, cudaMemcpyDeviceToHost);

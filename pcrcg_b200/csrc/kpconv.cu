@@ -8,7 +8,7 @@
 // Two stages: the AGGREGATION wf (this file) and the [Nq, K*Cin] x [K*Cin, Cout] CONTRACTION (gemm_tc.cu / gemm.cu) with the
 // 1/count row scale -- and optionally the InstanceNorm statistics of the result -- in its epilogue.  Aggregation kernels, in
 // dispatch order (kpconv_forward_dev / launch_agg):
-//   k_kpconv_aggregate_bf16p   features given as bf16 (hi, lo) planes, cin % 64 == 0, H <= 128 (two windows of 64): persistent, software-pipelined,
+//   k_kpconv_aggregate_bf16p   features given as bf16 (hi, lo) planes, cin % 64 == 0, H <= 64: persistent, software-pipelined,
 //                              ldmatrix + mma.sync m16n8k16 bf16x3, register stores in kperm64 slab order   (every production layer)
 //   k_kpconv_aggregate_bf16    same inputs, any H: one point per warp, 32-row staging, stmatrix transposed stores
 //   k_kpconv_aggregate_small   cin <= 4 (first layer): one thread per (point, kernel point)
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) k_kpconv_aggregate_bf16(
 // per warp is unchanged (2 buffers x 16 rows instead of 1 x 32), so residency stays at 5 CTAs / SM.
 constexpr int ABP_SMEM = AB_WARPS * ABP_WARP_BYTES;
 
-template <typename IdxT, int NWIN>
+template <typename IdxT>
 __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
     const float* __restrict__ q_pts, int nq, const float* __restrict__ s_pts, int ns, const IdxT* __restrict__ idx, int H,
     int idx_stride, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo, int cin, int ldxs,
@@ -843,14 +843,9 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
 {
     extern __shared__ __align__(16) uint8_t smem_b[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // A neighbour list wider than 64 (KITTI-shaped limits ~100) is walked as NWIN windows of 64: the unit of the software
-    // pipeline is (point, window); the accumulators are stored -- and the neighbour count written -- after a point's last window.
     const int stride = gridDim.x * AB_WARPS;
-    const int n_first = blockIdx.x * AB_WARPS + w;
-    if (n_first >= nq) return;
-    int u = 0;                                   // unit number of this warp: point n_first + (u / NWIN) * stride, window u % NWIN
-    auto pt_of = [&](int uu) -> int { return n_first + (NWIN == 1 ? uu : uu / NWIN) * stride; };
-    auto win_of = [&](int uu) -> int { return NWIN == 1 ? 0 : uu % NWIN; };
+    int n = blockIdx.x * AB_WARPS + w;
+    if (n >= nq) return;
     uint8_t* s_buf = smem_b + (size_t)w * ABP_WARP_BYTES;                    // buffer b: hi rows at b*BUF, lo rows at b*BUF + 16*PITCH
     float* s_xyz = reinterpret_cast<float*>(s_buf + 2 * ABP_BUF_BYTES);       // [2][16][4]
     const uint32_t a_buf = (uint32_t)__cvta_generic_to_shared(s_buf);
@@ -869,18 +864,15 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
 
     // neighbour indices of a point: the RAW values are requested early (load_raw) and only clamped to the shadow convention
     // when the point is about to start (clamp_idx), so the load latency hides behind the previous point's k-steps
-    auto load_raw = [&](int uu, IdxT& r0, IdxT& r1) {
-        const IdxT* row = idx + (size_t)min(pt_of(uu), nq - 1) * idx_stride;
-        const int h0 = 64 * win_of(uu) + lane;
-        r0 = row[h0 < H ? h0 : 0];
-        r1 = row[h0 + 32 < H ? h0 + 32 : 0];
+    auto load_raw = [&](int p, IdxT& r0, IdxT& r1) {
+        const IdxT* row = idx + (size_t)min(p, nq - 1) * idx_stride;
+        r0 = row[lane < H ? lane : 0];
+        r1 = row[lane + 32 < H ? lane + 32 : 0];
     };
-    auto clamp_idx = [&](int uu, IdxT r0, IdxT r1, int& j0, int& j1) {
+    auto clamp_idx = [&](int p, IdxT r0, IdxT r1, int& j0, int& j1) {
         const long long v0 = (long long)r0, v1 = (long long)r1;
-        const int h0 = 64 * win_of(uu) + lane;
-        const bool live = pt_of(uu) < nq;
-        j0 = (live && h0 < H && v0 >= 0 && v0 < ns) ? (int)v0 : ns;
-        j1 = (live && h0 + 32 < H && v1 >= 0 && v1 < ns) ? (int)v1 : ns;
+        j0 = (p < nq && lane < H && v0 >= 0 && v0 < ns) ? (int)v0 : ns;
+        j1 = (p < nq && lane + 32 < H && v1 >= 0 && v1 < ns) ? (int)v1 : ns;
     };
     // k-steps (of 16 neighbours) that hold at least one real neighbour, as a 4-bit mask
     auto step_mask = [&](int j0, int j1) -> uint32_t {
@@ -980,13 +972,12 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
     int j0, j1;
     {
         IdxT r0, r1;
-        load_raw(0, r0, r1);
-        clamp_idx(0, r0, r1, j0, j1);
+        load_raw(n, r0, r1);
+        clamp_idx(n, r0, r1, j0, j1);
     }
     uint32_t smask = step_mask(j0, j1);
     int s = smask ? __ffs(smask) - 1 : -1;
-    float qx = q_pts[3 * (size_t)n_first], qy = q_pts[3 * (size_t)n_first + 1], qz = q_pts[3 * (size_t)n_first + 2];
-    int cnt_acc = 0;
+    float qx = q_pts[3 * (size_t)n], qy = q_pts[3 * (size_t)n + 1], qz = q_pts[3 * (size_t)n + 2];
     int b = 0;
     if (s >= 0) {
         stage(j0, j1, s, 0);
@@ -996,15 +987,14 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
     }
 
     IdxT nr0, nr1;                               // raw neighbour indices of the next point (requested one point earlier)
-    load_raw(1, nr0, nr1);
-    while (pt_of(u) < nq) {
-        // requested now: neighbour indices of the unit AFTER the next one, query of the next unit, row flags of this one
-        const int n = pt_of(u), nn = u + 1;
-        const bool last_win = NWIN == 1 || win_of(u) == NWIN - 1;
+    load_raw(n + stride, nr0, nr1);
+    while (n < nq) {
+        // requested now: neighbour indices of the point AFTER the next one, query of the next point, row flags of this one
+        const int nn = n + stride;
         IdxT fr0, fr1;
-        load_raw(u + 2, fr0, fr1);
+        load_raw(nn + stride, fr0, fr1);
         int nj0 = ns, nj1 = ns;
-        const size_t qo = 3 * (size_t)min(pt_of(nn), nq - 1);
+        const size_t qo = 3 * (size_t)min(nn, nq - 1);
         const float nqx = q_pts[qo], nqy = q_pts[qo + 1], nqz = q_pts[qo + 2];
         uint8_t f0 = 0, f1 = 0;                  // row flags of this point's neighbours (compared when the point ends)
         if (blockIdx.y == 0) { f0 = rowflag[j0 < ns ? j0 : 0]; f1 = rowflag[j1 < ns ? j1 : 0]; }
@@ -1012,11 +1002,11 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
         int ns_first = -1;                       // first real k-step of the next point, once known
 
         if (s < 0) {
-            // a unit without any real neighbour: zero rows; nothing of the next unit is in flight yet
-            if (last_win) store_point(n);
+            // a point without any real neighbour: zero rows; nothing of the next point is in flight yet
+            store_point(n);
             clamp_idx(nn, nr0, nr1, nj0, nj1);
             nmask = step_mask(nj0, nj1);
-            ns_first = nmask ? __ffs(nmask) - 1 : -1;
+            ns_first = (nn < nq && nmask) ? __ffs(nmask) - 1 : -1;
             if (ns_first >= 0) {
                 stage(nj0, nj1, ns_first, b);
                 float x = 0.f, y = 0.f, z = 0.f;
@@ -1033,7 +1023,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
                 else {
                     clamp_idx(nn, nr0, nr1, nj0, nj1);
                     nmask = step_mask(nj0, nj1);
-                    ns_first = nmask ? __ffs(nmask) - 1 : -1;
+                    ns_first = (nn < nq && nmask) ? __ffs(nmask) - 1 : -1;
                     s2 = ns_first;
                 }
                 float x = 0.f, y = 0.f, z = 0.f;
@@ -1053,17 +1043,14 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 5) k_kpconv_aggregate_bf16p(
                 s = s2;
                 b ^= 1;
             }
-            if (last_win) store_point(n);
-            b ^= 1;                              // the next unit's first k-step is in flight in the other buffer
+            store_point(n);
+            b ^= 1;                              // the next point's first k-step is in flight in the other buffer
         }
         if (blockIdx.y == 0) {
-            cnt_acc += __popc(__ballot_sync(0xffffffffu, j0 < ns && f0 != 0)) + __popc(__ballot_sync(0xffffffffu, j1 < ns && f1 != 0));
-            if (last_win) {
-                if (lane == 0) inv_cnt[n] = 1.0f / (float)(cnt_acc > 1 ? cnt_acc : 1);
-                cnt_acc = 0;
-            }
+            const int cnt = __popc(__ballot_sync(0xffffffffu, j0 < ns && f0 != 0)) + __popc(__ballot_sync(0xffffffffu, j1 < ns && f1 != 0));
+            if (lane == 0) inv_cnt[n] = 1.0f / (float)(cnt > 1 ? cnt : 1);
         }
-        u = nn;
+        n = nn;
         j0 = nj0; j1 = nj1;
         nr0 = fr0; nr1 = fr1;
         qx = nqx; qy = nqy; qz = nqz;
@@ -1252,7 +1239,7 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
     // which aggregation kernel runs (the same for every chunk): bf16 planes -> ldmatrix kernels; the pipelined one writes its
     // 64-channel slabs in kperm64 order, so the weights are split with the matching K permutation
     const bool planes = tc && x_hi != nullptr && x_lo != nullptr && cin % 64 == 0 && ldxs >= cin && ldxs % 8 == 0 && !g_agg_simt && ns > 0;
-    const bool pipelined = planes && g_agg_pipelined && H <= 128;       // two 64-neighbour windows beyond 64
+    const bool pipelined = planes && g_agg_pipelined && H <= 64;
     const bool fused = pipelined && g_fused > 0 && kpconv_fused_shape_ok(nq, ns, H, cin, cout, K, ldxs) &&
                        (g_fused > 1 || (cin == 64 && cout == 64));
     if (tail1) {
@@ -1302,12 +1289,12 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
                 __nv_bfloat16* th = wf_hi + (size_t)K * cin_m;
                 __nv_bfloat16* tl = wf_lo + (size_t)K * cin_m;
                 if (idx_is_i64) {
-                    k_kpconv_aggregate_bf16p<long long, 1><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
+                    k_kpconv_aggregate_bf16p<long long><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
                         t_hi, t_lo, cin_m, cin_m, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
                     k_kpconv_aggregate_small<long long, 1, true><<<(unsigned)cdiv64(rows, 16), 256, 0, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H,
                         idx_stride, x + cin_m, cin, rowflag, kpts, K, inv_extent, nullptr, th, tl, ldk, inv_cnt + r0);
                 } else {
-                    k_kpconv_aggregate_bf16p<int, 1><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
+                    k_kpconv_aggregate_bf16p<int><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
                         t_hi, t_lo, cin_m, cin_m, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
                     k_kpconv_aggregate_small<int, 1, true><<<(unsigned)cdiv64(rows, 16), 256, 0, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H,
                         idx_stride, x + cin_m, cin, rowflag, kpts, K, inv_extent, nullptr, th, tl, ldk, inv_cnt + r0);
@@ -1320,11 +1307,12 @@ int kpconv_forward_dev(const float* q_pts, int64_t nq, const float* s_pts, int64
                 unsigned gx = (unsigned)cdiv64(kNumSMs * 5, gy);
                 if ((int64_t)gx > cdiv64(rows, AB_WARPS)) gx = (unsigned)cdiv64(rows, AB_WARPS);
                 dim3 grid(gx, gy);
-#define PCRCG_AGG_P(T_, W_) k_kpconv_aggregate_bf16p<T_, W_><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const T_*)ip, H, idx_stride, \
-                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0)
-                if (idx_is_i64) { if (H <= 64) PCRCG_AGG_P(long long, 1); else PCRCG_AGG_P(long long, 2); }
-                else { if (H <= 64) PCRCG_AGG_P(int, 1); else PCRCG_AGG_P(int, 2); }
-#undef PCRCG_AGG_P
+                if (idx_is_i64)
+                    k_kpconv_aggregate_bf16p<long long><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const long long*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
+                else
+                    k_kpconv_aggregate_bf16p<int><<<grid, AB_WARPS * 32, ABP_SMEM, st>>>(qp, rows, s_pts, (int)ns, (const int*)ip, H, idx_stride,
+                        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, cin, ldxs, rowflag, kpts, K, inv_extent, wf_hi, wf_lo, ldk, inv_cnt + r0);
                 rc = cudaGetLastError() == cudaSuccess ? PCRCG_OK : PCRCG_ERR;
                 if (rc) set_error("kpconv: pipelined bf16 aggregate launch failed");
             } else if (planes) {

@@ -115,23 +115,37 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const float* __restrict__ 
                                                       const int32_t* __restrict__ starts, int nb, uint2* __restrict__ cells,
                                                       uint32_t* __restrict__ ncells)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns) return;
-    const uint32_t sl = slot[i];
-    const uint32_t st = cell_start[sl];
-    const uint32_t k = atomicAdd(&cursor[sl], 1u);
-    rec[st + k] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
-    if (k == 0) {
-        const uint32_t en = cell_start[sl + 1];
-        range[sl] = make_uint2(st, en);
-        // work units of the cell-centric search: (cell, chunk of RQ_QCHUNK of its points), in arbitrary order.  A unit packs
-        // the cloud (16 bits) with the chunk number; cells of a query set binned into a coarser grid hold ~50 points, and
-        // one warp per such cell would leave most of the machine idle at the small pyramid levels.
-        const uint32_t nu = (en - st + RQ_QCHUNK - 1) / RQ_QCHUNK;
-        const uint32_t cl = (uint32_t)cloud_of(starts, nb, i);
-        const uint32_t base = atomicAdd(ncells, nu);
-        for (uint32_t u = 0; u < nu; u++) cells[base + u] = make_uint2(sl, cl | (u << 16));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t sl = 0, nu = 0, cl = 0;
+    if (i < ns) {
+        sl = slot[i];
+        const uint32_t st = cell_start[sl];
+        const uint32_t k = atomicAdd(&cursor[sl], 1u);
+        rec[st + k] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
+        if (k == 0) {
+            const uint32_t en = cell_start[sl + 1];
+            range[sl] = make_uint2(st, en);
+            // work units of the cell-centric search: (cell, chunk of RQ_QCHUNK of its points), in arbitrary order.  A unit packs
+            // the cloud (16 bits) with the chunk number; cells of a query set binned into a coarser grid hold ~50 points, and
+            // one warp per such cell would leave most of the machine idle at the small pyramid levels.
+            nu = (en - st + RQ_QCHUNK - 1) / RQ_QCHUNK;
+            cl = (uint32_t)cloud_of(starts, nb, i);
+        }
     }
+    // one atomic per warp: exclusive prefix of the lanes' unit counts (a plain atomicAdd of a per-lane amount on one
+    // address is not warp-aggregated by the compiler: measured 183 us against 72 us for the 1.25 M-point grid)
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = nu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(ncells, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - nu;
+    for (uint32_t u = 0; u < nu; u++) cells[base + u] = make_uint2(sl, cl | (u << 16));
 }
 
 __device__ __forceinline__ float d2_ref(float qx, float qy, float qz, float4 p)
@@ -501,8 +515,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_radius_cells(
         }
         __syncwarp();
 
+        float4 qnext = qrec[qr.x];                                  // a unit holds >= 1 query; the next record is requested one query ahead
         for (uint32_t qi = qr.x; qi < qr.y; qi++) {
-            const float4 qp = qrec[qi];
+            const float4 qp = qnext;
+            if (qi + 1 < qr.y) qnext = qrec[qi + 1];
             const float qx = qp.x, qy = qp.y, qz = qp.z;
             const int i = (int)__float_as_uint(qp.w);
             int nm = 0;
@@ -795,11 +811,12 @@ int radius_query_cells_dev(const float* q, int64_t nq, const int32_t* q_lens, in
     }
     if (maxcount) PCRCG_CUDA(cudaMemsetAsync(maxcount, 0, sizeof(int32_t), st));
     const float r2 = radius * radius;      // neighbors.cpp:226 (fp32 product)
-    // capacities follow the list width: the limits are the 80 % quantile of the neighbour counts (calibrate_neighbors), so wide
-    // lists mean dense neighbourhoods (KITTI-shaped: ~100 hits among ~650 candidates)
-    if (width > 0 && width <= 48)
-        return launch_cells<384, 128, 8>(qg, koff, r, r2, (int)ns, width, row_stride, rows, counts, maxcount, nq, st);
-    return launch_cells<1024, 256, 4>(qg, koff, r, r2, (int)ns, width, row_stride, rows, counts, maxcount, nq, st);
+    return launch_cells<384, 128, 8>(qg, koff, r, r2, (int)ns, width, row_stride, rows, counts, maxcount, nq, st);
 }
+
+// width <= 48 (3DMatch-shaped limits 33-42): cell-centric.  Wider lists mean dense neighbourhoods (the limits are the 80 %
+// quantile of the neighbour counts: KITTI-shaped ~100 hits among ~650 candidates): a 1024-candidate / 256-hit configuration of
+// the cell kernel fits only 12 warps per SM and measured 6.1 ms per 32-pair KITTI step against 4.5 ms for one warp per query.
+bool radius_cells_preferred(int32_t width) { return width > 0 && width <= 48; }
 
 }  // namespace pcrcg
