@@ -163,48 +163,93 @@ def cpu_reference_run(pairs, cfg, limits, state_dict, threads, views_np=None):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed regions.  In-process NVML (nvidia_ml_py) from a thread: spawning
+    `nvidia-smi -lms` next to the pipelined loops stalls this process's CUDA calls (its start-up ~130 ms, each of its queries up
+    to ~30 ms: measured as gaps between submissions), an NVML query here takes ~0.1 ms.  Falls back to nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (t, sm_mhz, max_mhz, [reasons])
+        self.stop_flag = False
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        try:
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            smax = None
+        while not self.stop_flag:
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.lines.append((time.perf_counter(), clk, smax, [n for b, n in self.REASONS if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.lines:
-            f = [x.strip() for x in line.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
                 clk, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            smax = mx
+            rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]) if v.lower().startswith("active")]
+            self.lines.append((time.perf_counter(), clk, mx, rs))
+
+    def stop(self, t_begin, t_end):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.12)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, clk, mx, rs in self.lines:
+            smax = mx if mx is not None else smax
             if t_begin <= ts <= t_end + 0.2:
                 sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+                reasons.update(rs)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "NVML in process, 50 ms period" if self.mode == "nvml" else "nvidia-smi -lms 250"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,9 +323,13 @@ def quick_measure(workload, P, K, W, rank, world, dev, flush, dist):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    hs = []
+    for i in range(K):
+        if i >= 2:
+            hs[i - 2].ready.synchronize()
         flush.fill_(0.0)
-        y, _ = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
+        hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
+    y, _ = hs[-1].result()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -443,6 +492,9 @@ def main():
     out_bufs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
     for i in range(2):
         path.run_host(pts_host, lens_host, out_bufs[i], views_e2e)
+    wh = [path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev) for _ in range(2)]     # two steps in flight once (allocator warm-up)
+    wh[-1].result()
+    torch.cuda.synchronize()
     work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder, views_dev)
 
     # ---- parity of THIS batch, outside every timed region: one pair of the stacked run vs the reference run on that pair
@@ -476,12 +528,23 @@ def main():
     t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    hs = []
+    dbg_t = []
+    for i in range(K):
+        if i >= 2:
+            hs[i - 2].ready.synchronize()                 # at most two steps in flight (bounds memory, as in the e2e loop)
+        dbg_t.append(time.perf_counter())
         flush.fill_(0.0)                                  # L2 flush between timed iterations
-        y, _ = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
+        # asynchronous submission: the pyramid of step i+1 (and its host-side size read-backs) overlaps the encoder of step i
+        hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
+    y, _ = hs[-1].result()                                # the encoder stream is in order: the last result ends the region
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    if os.environ.get("PCRCG_BENCH_DEBUG"):
+        st = torch.cuda.memory_stats()
+        print("[debug] host ms between submissions:", [round(1000 * (b - a), 1) for a, b in zip(dbg_t, dbg_t[1:])],
+              "cudaMalloc", st["num_device_alloc"], "cudaFree", st["num_device_free"], "retries", st["num_alloc_retries"], file=sys.stderr)
     launches = int(L.pcrcg_launch_count() - launches0)
     # per-class device time: the same K steps once more with the library's event pairs around every kernel class (kept out of
     # the region that defines `value`: ~300 extra event records per step are host work the product path does not do)

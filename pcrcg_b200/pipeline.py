@@ -52,16 +52,50 @@ class FeaturePath:
 
     @torch.no_grad()
     def run_device(self, points, lengths, features=None, views_per_cloud=None):
-        """points [N,3] f32 cuda, lengths [2P] i32 cuda -> (features of the coarsest level [N3, C], batch dict).
-        views_per_cloud (colour path, in_feats_dim = C2d + 1): per cloud its RGB-D views in write order (see
-        projection.unproject_features_batch); the 2D features are un-projected onto the points and form the input rows."""
-        if views_per_cloud is not None:
-            from . import projection
-            features = projection.unproject_features_batch(points, lengths, views_per_cloud)
-        batch = dataloader.build_pyramid(points, lengths, self.config, self.limits, device=self.device)
-        if features is None:
-            features = torch.ones((points.shape[0], self.config.in_feats_dim), dtype=torch.float32, device=self.device)
-        return self.encoder(features, batch), batch
+        """points [N,3] f32 cuda, lengths [2P] i32 cuda -> (features of the coarsest level [N3, C], batch dict), ready on the
+        caller's current stream.  views_per_cloud (colour path, in_feats_dim = C2d + 1): per cloud its RGB-D views in write
+        order (see projection.unproject_features_batch); the 2D features are un-projected onto the points and form the input
+        rows."""
+        return self.submit_device(points, lengths, features, views_per_cloud).result()
+
+    def _streams(self):
+        if not hasattr(self, "_s_pyr"):
+            self._s_pyr = torch.cuda.Stream(device=self.device)
+            self._s_enc = torch.cuda.Stream(device=self.device)
+        return self._s_pyr, self._s_enc
+
+    @torch.no_grad()
+    def submit_device(self, points, lengths, features=None, views_per_cloud=None):
+        """Asynchronous form of :meth:`run_device`: the pyramid (subsampling + searches, whose size read-backs block the host)
+        runs on one stream and the encoder on another, so the pyramid of the NEXT submission -- and its host waits -- overlaps
+        the encoder of this one instead of draining the GPU four times per step.  ``handle.result()`` makes the caller's
+        current stream wait for the encoder and returns (features, batch)."""
+        cur = torch.cuda.current_stream(self.device)
+        sp, se = self._streams()
+        ev_in = torch.cuda.Event()
+        ev_in.record(cur)
+        sp.wait_event(ev_in)
+        with torch.cuda.stream(sp):
+            if views_per_cloud is not None:
+                from . import projection
+                features = projection.unproject_features_batch(points, lengths, views_per_cloud)
+            batch = dataloader.build_pyramid(points, lengths, self.config, self.limits, device=self.device)
+            if features is None:
+                features = torch.ones((points.shape[0], self.config.in_feats_dim), dtype=torch.float32, device=self.device)
+            ev_p = torch.cuda.Event()
+            ev_p.record(sp)
+        se.wait_event(ev_p)
+        with torch.cuda.stream(se):
+            y = self.encoder(features, batch)
+            ev_e = torch.cuda.Event()
+            ev_e.record(se)
+        # tensors of one stream's allocator pool that another stream reads
+        for t in [points, lengths, features] + [x for k in ("points", "neighbors", "pools", "upsamples", "stack_lengths", "pair_segments")
+                                                for x in batch[k]]:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(sp)
+                t.record_stream(se)
+        return _DeviceResult(y, batch, ev_e, self.device)
 
     @torch.no_grad()
     def run_host(self, points_host, lengths_host, out_host=None, views_per_cloud=None):
@@ -81,10 +115,9 @@ class FeaturePath:
             self._pinned_small, self._slot = {}, 0
         pts = points_host.to(self.device, non_blocking=True)
         lens = lengths_host.to(self.device, non_blocking=True)
-        y, batch = self.run_device(pts, lens, views_per_cloud=views_per_cloud)
+        h = self.submit_device(pts, lens, views_per_cloud=views_per_cloud)
+        y, batch, ready = h.y, h.batch, h.ready
         coarse_dev = batch["stack_lengths"][-1]
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(ready)
             if out_host is not None and out_host.shape[0] >= y.shape[0]:
@@ -96,7 +129,7 @@ class FeaturePath:
             step = max(1, (4 << 20) // max(1, y.shape[1] * 4))
             for r in range(0, y.shape[0], step):
                 out[r:r + step].copy_(y[r:r + step], non_blocking=True)
-            self._slot ^= 1                      # small pinned staging buffers are cached (pinned allocation is slow)
+            self._slot = (self._slot + 1) % 4    # small pinned staging buffers are cached (pinned allocation is slow); 4 in flight
             key = (self._slot, tuple(coarse_dev.shape))
             if key not in self._pinned_small:
                 self._pinned_small[key] = torch.empty(coarse_dev.shape, dtype=coarse_dev.dtype, pin_memory=True)
@@ -107,6 +140,17 @@ class FeaturePath:
             done = torch.cuda.Event()
             done.record(self._copy_stream)
         return _HostResult(out, coarse, done)
+
+
+class _DeviceResult:
+    def __init__(self, y, batch, ready, device):
+        self.y, self.batch, self.ready, self._device = y, batch, ready, device
+
+    def result(self):
+        cur = torch.cuda.current_stream(self._device)
+        cur.wait_event(self.ready)
+        self.y.record_stream(cur)
+        return self.y, self.batch
 
 
 class _HostResult:
