@@ -24,6 +24,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The CPU legs (cpu_baseline, parity_check) run PyTorch-CPU / OpenMP code in this process; by default its worker threads keep
+# spinning for ~200 ms after a parallel region, on every core, which starves the thread that launches the GPU kernels of the
+# timed loops (measured as 100-400 ms gaps between submissions).  Workers sleep instead.
+os.environ.setdefault("KMP_BLOCKTIME", "0")
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 import numpy as np  # noqa: E402
 
@@ -497,28 +502,6 @@ def main():
     torch.cuda.synchronize()
     work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder, views_dev)
 
-    # ---- parity of THIS batch, outside every timed region: one pair of the stacked run vs the reference run on that pair
-    # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
-    parity = None
-    if rank == 0 and not args.no_parity_check:
-        from oracle import checks
-        kq = min(args.parity_pair, P - 1)
-        cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
-        n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
-        seg = batch["pair_segments"][-1].cpu().tolist()
-        x_cpu, x_equal = None, None
-        if views_np is not None:                          # colour: the un-projected input rows of the pair, bit for bit
-            from pcrcg_b200 import projection
-            x_cpu = cpu_unproject(pairs[kq], views_np[2 * kq:2 * kq + 2])
-            x_dev = projection.unproject_features_batch(pts_dev, lens_dev, views_dev)
-            st0 = int(batch["pair_segments"][0][kq].item())
-            x_equal = bool(np.array_equal(x_dev[st0:st0 + x_cpu.shape[0]].cpu().numpy(), x_cpu))
-        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg, x=x_cpu)
-        parity = {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
-                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "unprojected_rows_equal": x_equal,
-                  "ok": (not bad) and enc_err < 1e-3 and x_equal is not False,
-                  "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
-
     # ---- device-resident timed region ----------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -537,7 +520,7 @@ def main():
         flush.fill_(0.0)                                  # L2 flush between timed iterations
         # asynchronous submission: the pyramid of step i+1 (and its host-side size read-backs) overlaps the encoder of step i
         hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
-    y, _ = hs[-1].result()                                # the encoder stream is in order: the last result ends the region
+    y, batch = hs[-1].result()                            # the encoder stream is in order: the last result ends the region
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -592,6 +575,28 @@ def main():
         for item in args.extra_workloads.split(","):
             wl, _, pp_ = item.partition(":")
             extras.append(quick_measure(wl, int(pp_ or 16), max(3, min(K, 5)), 3, rank, world, dev, flush, dist if world > 1 else None))
+
+    # ---- parity of THIS batch, AFTER every timed region (its CPU work must not disturb them): one pair of the stacked run vs the reference run on that pair
+    # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        from oracle import checks
+        kq = min(args.parity_pair, P - 1)
+        cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
+        n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
+        seg = batch["pair_segments"][-1].cpu().tolist()
+        x_cpu, x_equal = None, None
+        if views_np is not None:                          # colour: the un-projected input rows of the pair, bit for bit
+            from pcrcg_b200 import projection
+            x_cpu = cpu_unproject(pairs[kq], views_np[2 * kq:2 * kq + 2])
+            x_dev = projection.unproject_features_batch(pts_dev, lens_dev, views_dev)
+            st0 = int(batch["pair_segments"][0][kq].item())
+            x_equal = bool(np.array_equal(x_dev[st0:st0 + x_cpu.shape[0]].cpu().numpy(), x_cpu))
+        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg, x=x_cpu)
+        parity = {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
+                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "unprojected_rows_equal": x_equal,
+                  "ok": (not bad) and enc_err < 1e-3 and x_equal is not False,
+                  "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
 
     if rank == 0:
         peaks = {}

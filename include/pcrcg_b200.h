@@ -168,6 +168,13 @@ int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
                        float* out, void* split_hi, void* split_lo, int32_t split_ld, uint8_t* row_positive,
                        pcrcg_stream_t stream);
 
+/* The same with the SHORTCUT given as bf16 (hi, lo) planes [n, sc_ld] (sc = hi + lo): a block output that was emitted as
+ * planes only (its fp32 copy never written) feeding the next block's residual sum.  Needs C % 4 == 0. */
+int pcrcg_norm_act_planes_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
+                              const float* rstd, const void* sc_hi, const void* sc_lo, int32_t sc_ld, const float* sc_mean,
+                              const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo, int32_t split_ld,
+                              uint8_t* row_positive, pcrcg_stream_t stream);
+
 /* Descriptor head (models/architectures.py:572-582, "next" row of the scope table): x [n, F+2] ->
  * feats [n,F] = x[:, :F] / max(|x[:, :F]|_2, 1e-12); overlap / saliency [n] = clamp(sigmoid(x[:, F | F+1]), 0, 1), NaN/Inf -> 0 */
 int pcrcg_descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency,
@@ -220,6 +227,11 @@ int pcrcg_mutual_dev(const int32_t* row_best, const int32_t* col_best, int64_t n
 /* max_pool (models/blocks.py:86-102) and closest_pool (:71-83): x [ns,C], inds [nq,H] -> out [nq,C] */
 int pcrcg_max_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq, int32_t H,
                        int32_t idx_stride, float* out, pcrcg_stream_t stream);
+/* max_pool of features held as bf16 (hi, lo) planes [ns, ldx] -> planes [nq, ldo]: an entry's value is hi + lo, the
+ * winner's pair is copied (the output represents the maximum exactly); a shadow index contributes 0.  C % 4 == 0. */
+int pcrcg_max_pool_planes_dev(const void* x_hi, const void* x_lo, int64_t ns, int32_t C, int32_t ldx, const void* inds,
+                              int32_t idx_is_i64, int64_t nq, int32_t H, int32_t idx_stride, void* out_hi, void* out_lo, int32_t ldo,
+                              pcrcg_stream_t stream);
 int pcrcg_closest_pool_dev(const float* x, int64_t ns, int32_t C, const void* inds, int32_t idx_is_i64, int64_t nq,
                            int32_t idx_stride, float* out, pcrcg_stream_t stream);
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "pcrcg_gemm_force_simt": (None, [_I32]),
     "pcrcg_colstats_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _F, _P, _P, _P]),
     "pcrcg_norm_act_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I32, _P, _P]),
+    "pcrcg_norm_act_planes_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _F, _P, _P, _P, _I32, _P, _P]),
+    "pcrcg_max_pool_planes_dev": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _I32, _P]),
     "pcrcg_descriptor_head_dev": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),
     "pcrcg_max_pool_dev": (C.c_int, [_P, _I64, _I32, _P, _I32, _I64, _I32, _I32, _P, _P]),
     "pcrcg_projection_ws_bytes": (_SZ, [_I64]),

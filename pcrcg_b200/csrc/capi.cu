@@ -80,6 +80,10 @@ int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float,
 int norm_act_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
                  const float*, float, float*, void*, void*, int32_t, uint8_t*, cudaStream_t);
 int max_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, int32_t, float*, cudaStream_t);
+int max_pool_planes_dev(const void*, const void*, int64_t, int32_t, int32_t, const void*, int, int64_t, int32_t, int32_t, void*, void*, int32_t,
+                        cudaStream_t);
+int norm_act_planes_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, const float*, const float*, const float*, const float*,
+                        const float*, float, float*, void*, void*, int32_t, uint8_t*, const void*, const void*, int32_t, cudaStream_t);
 int descriptor_head_dev(const float*, int64_t, int32_t, float*, float*, float*, cudaStream_t);
 int closest_pool_dev(const float*, int64_t, int32_t, const void*, int, int64_t, int32_t, float*, cudaStream_t);
 
@@ -340,6 +344,21 @@ int pcrcg_norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_
 {
     return norm_act_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld, row_positive,
                         (cudaStream_t)stream);
+}
+
+int pcrcg_norm_act_planes_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean,
+                              const float* rstd, const void* sc_hi, const void* sc_lo, int32_t sc_ld, const float* sc_mean, const float* sc_rstd,
+                              float slope, float* out, void* split_hi, void* split_lo, int32_t split_ld, uint8_t* row_positive,
+                              pcrcg_stream_t stream)
+{
+    return norm_act_planes_dev(x, n, C, seg_starts, nseg, mean, rstd, nullptr, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld,
+                               row_positive, sc_hi, sc_lo, sc_ld, (cudaStream_t)stream);
+}
+
+int pcrcg_max_pool_planes_dev(const void* x_hi, const void* x_lo, int64_t ns, int32_t C, int32_t ldx, const void* inds, int32_t idx_is_i64,
+                              int64_t nq, int32_t H, int32_t idx_stride, void* out_hi, void* out_lo, int32_t ldo, pcrcg_stream_t stream)
+{
+    return max_pool_planes_dev(x_hi, x_lo, ns, C, ldx, inds, idx_is_i64, nq, H, idx_stride, out_hi, out_lo, ldo, (cudaStream_t)stream);
 }
 
 int pcrcg_descriptor_head_dev(const float* x, int64_t n, int32_t F, float* feats, float* overlap, float* saliency, pcrcg_stream_t stream)

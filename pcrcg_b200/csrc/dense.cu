@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(256, MINB) k_norm_act_v4(const float* __restri
                                                      const float* __restrict__ sc, const float* __restrict__ sc_mean,
                                                      const float* __restrict__ sc_rstd, float slope, float* __restrict__ out,
                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int lds,
-                                                     int tcols, int trows, uint8_t* __restrict__ rowflag)
+                                                     int tcols, int trows, uint8_t* __restrict__ rowflag,
+                                                     const __nv_bfloat16* __restrict__ sc_hi, const __nv_bfloat16* __restrict__ sc_lo, int sc_lds)
 {
     const int c4 = C >> 2;
     float rsum[NA_UNROLL];
@@ -143,6 +144,13 @@ __global__ void __launch_bounds__(256, MINB) k_norm_act_v4(const float* __restri
             if (rr[u] < n) {
                 v[u] = *reinterpret_cast<const float4*>(x + (size_t)rr[u] * C + 4 * cg);
                 if (sc) s[u] = *reinterpret_cast<const float4*>(sc + (size_t)rr[u] * C + 4 * cg);
+                else if (sc_hi) {
+                    // the shortcut exists only as bf16 (hi, lo) planes (a block output whose fp32 copy was never written)
+                    const uint2 a = *reinterpret_cast<const uint2*>(sc_hi + (size_t)rr[u] * sc_lds + 4 * cg);
+                    const uint2 b = *reinterpret_cast<const uint2*>(sc_lo + (size_t)rr[u] * sc_lds + 4 * cg);
+                    s[u] = make_float4(__uint_as_float(a.x << 16) + __uint_as_float(b.x << 16), __uint_as_float(a.x & 0xffff0000u) + __uint_as_float(b.x & 0xffff0000u),
+                                       __uint_as_float(a.y << 16) + __uint_as_float(b.y << 16), __uint_as_float(a.y & 0xffff0000u) + __uint_as_float(b.y & 0xffff0000u));
+                }
             }
         }
         int seg = -1;
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(256, MINB) k_norm_act_v4(const float* __restri
                 }
             }
             float4 o = na_apply(v[u], mu, rs);
-            if (sc) {
+            if (sc || sc_hi) {
                 const float4 t = na_apply(s[u], smu, srs);
                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
             }
@@ -243,6 +251,50 @@ __global__ void __launch_bounds__(256) k_max_pool(const float* __restrict__ x, i
     }
 }
 
+// max_pool of features that exist as bf16 (hi, lo) planes: the value of an entry is hi + lo (exact in fp32); the winner's
+// (hi, lo) pair is copied, so the output planes represent the maximum exactly; a shadow index contributes (0, 0).
+template <typename IdxT>
+__global__ void __launch_bounds__(256) k_max_pool_planes(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo, int ns,
+                                                         int C, int ldx, const IdxT* __restrict__ idx, int nq, int H, int idx_stride,
+                                                         __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, int ldo)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= nq) return;
+    const IdxT* row = idx + (size_t)n * idx_stride;
+    for (int cb = 0; cb < C; cb += 128) {                   // warp-uniform trip counts (shuffles inside)
+        const int c = cb + 4 * lane;
+        const bool act = c < C;
+        float m[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+        uint32_t bh[4] = { 0, 0, 0, 0 }, bl[4] = { 0, 0, 0, 0 };          // winner's hi / lo patterns (upper 16 bits)
+        for (int h0 = 0; h0 < H; h0 += 32) {
+            int jl = ns;
+            if (h0 + lane < H) { long long v = (long long)row[h0 + lane]; jl = (v >= 0 && v < ns) ? (int)v : ns; }
+            const int hn = min(32, H - h0);
+#pragma unroll 4
+            for (int h = 0; h < hn; h++) {
+                const int j = __shfl_sync(0xffffffffu, jl, h);
+                uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+                if (act && j < ns) {
+                    a = __ldg(reinterpret_cast<const uint2*>(x_hi + (size_t)j * ldx + c));
+                    b = __ldg(reinterpret_cast<const uint2*>(x_lo + (size_t)j * ldx + c));
+                }
+                const uint32_t ah[4] = { a.x << 16, a.x & 0xffff0000u, a.y << 16, a.y & 0xffff0000u };
+                const uint32_t al[4] = { b.x << 16, b.x & 0xffff0000u, b.y << 16, b.y & 0xffff0000u };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float v = __uint_as_float(ah[k]) + __uint_as_float(al[k]);
+                    if (v > m[k]) { m[k] = v; bh[k] = ah[k]; bl[k] = al[k]; }
+                }
+            }
+        }
+        if (act) {
+            *reinterpret_cast<uint2*>(o_hi + (size_t)n * ldo + c) = make_uint2((bh[0] >> 16) | bh[1], (bh[2] >> 16) | bh[3]);
+            *reinterpret_cast<uint2*>(o_lo + (size_t)n * ldo + c) = make_uint2((bl[0] >> 16) | bl[1], (bl[2] >> 16) | bl[3]);
+        }
+    }
+}
+
 // x_pad[idx[n,0]]   (models/blocks.py:71-83)
 template <typename IdxT>
 __global__ void __launch_bounds__(256) k_closest_pool(const float* __restrict__ x, int ns, int C, int ldx, const IdxT* __restrict__ idx,
@@ -313,11 +365,26 @@ int colstats_final_dev(const double* acc, const int32_t* seg_starts, int32_t nse
     return PCRCG_OK;
 }
 
+int norm_act_planes_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
+                        const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
+                        int32_t split_ld, uint8_t* rowflag, const void* sc_hi, const void* sc_lo, int32_t sc_ld, cudaStream_t st);
+
 int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
                  const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
                  int32_t split_ld, uint8_t* rowflag, cudaStream_t st)
 {
+    return norm_act_planes_dev(x, n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, split_hi, split_lo, split_ld, rowflag,
+                               nullptr, nullptr, 0, st);
+}
+
+// sc_hi / sc_lo (optional, instead of sc): the shortcut as bf16 (hi, lo) planes, row pitch sc_ld
+int norm_act_planes_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts, int32_t nseg, const float* mean, const float* rstd,
+                        const float* sc, const float* sc_mean, const float* sc_rstd, float slope, float* out, void* split_hi, void* split_lo,
+                        int32_t split_ld, uint8_t* rowflag, const void* sc_hi, const void* sc_lo, int32_t sc_ld, cudaStream_t st)
+{
     if (n == 0) return PCRCG_OK;
+    PCRCG_REQUIRE(sc_hi == nullptr || (sc == nullptr && sc_lo != nullptr && sc_ld % 8 == 0 && sc_ld >= C && C % 4 == 0 && n < (1ll << 31) && g_norm_v4),
+                  "norm_act: a plane shortcut needs C %% 4 == 0, both planes and no fp32 shortcut");
     PCRCG_REQUIRE(split_hi == nullptr || (split_lo != nullptr && split_ld % 8 == 0 && split_ld >= C), "norm_act: bad split geometry");
     PCRCG_REQUIRE(out != nullptr || split_hi != nullptr, "norm_act: no output requested (out and the split planes are both NULL)");
     ProfScope prof(PC_NORM, st, 1);
@@ -329,7 +396,7 @@ int norm_act_dev(const float* x, int64_t n, int32_t C, const int32_t* seg_starts
         PCRCG_REQUIRE(rowflag == nullptr || flag_ok, "norm_act: row flags need a power-of-two channel count");
 #define PCRCG_NA(U_, B_) k_norm_act_v4<U_, B_><<<(unsigned)cdiv64(n, trows * U_), 256, 0, st>>>( \
             x, (int)n, C, seg_starts, nseg, mean, rstd, sc, sc_mean, sc_rstd, slope, out, (__nv_bfloat16*)split_hi, (__nv_bfloat16*)split_lo, \
-            split_ld, tcols, trows, rowflag)
+            split_ld, tcols, trows, rowflag, (const __nv_bfloat16*)sc_hi, (const __nv_bfloat16*)sc_lo, sc_ld)
         // launch shape measured per case on B200 (tools/bench_norm_apply.py): the row-flag mode (narrow tensors, extra shuffles)
         // prefers more resident warps, the plain streaming mode more loads in flight per thread
         switch (g_norm_variant > 0 ? g_norm_variant : (rowflag != nullptr ? 4 : 2)) {
@@ -368,6 +435,23 @@ int max_pool_dev(const float* x, int64_t ns, int32_t C, const void* idx, int idx
     unsigned g = (unsigned)cdiv64(nq, 8);
     if (idx_is_i64) k_max_pool<long long><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const long long*)idx, (int)nq, H, idx_stride, out);
     else k_max_pool<int><<<g, 256, 0, st>>>(x, (int)ns, C, C, (const int*)idx, (int)nq, H, idx_stride, out);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+int max_pool_planes_dev(const void* x_hi, const void* x_lo, int64_t ns, int32_t C, int32_t ldx, const void* idx, int idx_is_i64, int64_t nq,
+                        int32_t H, int32_t idx_stride, void* o_hi, void* o_lo, int32_t ldo, cudaStream_t st)
+{
+    PCRCG_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ldx >= C && ldo >= C, "max_pool (planes): C and the row pitches must be multiples of 4");
+    if (nq == 0) return PCRCG_OK;
+    ProfScope prof(PC_POOL, st, 1);
+    const unsigned g = (unsigned)cdiv64(nq, 8);
+    if (idx_is_i64)
+        k_max_pool_planes<long long><<<g, 256, 0, st>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (int)ns, C, ldx, (const long long*)idx,
+                                                        (int)nq, H, idx_stride, (__nv_bfloat16*)o_hi, (__nv_bfloat16*)o_lo, ldo);
+    else
+        k_max_pool_planes<int><<<g, 256, 0, st>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (int)ns, C, ldx, (const int*)idx, (int)nq,
+                                                  H, idx_stride, (__nv_bfloat16*)o_hi, (__nv_bfloat16*)o_lo, ldo);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

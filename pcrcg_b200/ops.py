@@ -31,7 +31,7 @@ def _ws(nbytes, device):
 # Derived data that rides on a tensor as Python attributes (the bf16 planes of its values, its InstanceNorm statistics, its
 # row-positive flags) is stamped with the tensor's version counter and ignored once an in-place update has changed the
 # values.  Ops of this module that write in place through the C library (which the counter does not see) strip it.
-_DERIVED = ("_pcrcg_stats", "_pcrcg_split", "_pcrcg_rowpos")
+_DERIVED = ("_pcrcg_stats", "_pcrcg_split", "_pcrcg_rowpos", "_pcrcg_wsplit")
 
 
 def _attach(t, name, value):
@@ -255,8 +255,17 @@ def linear(x, weight, stat_segments=False):
     with torch.cuda.device(x.device):
         if sp is not None and not _force_simt and cout % 16 == 0 and cin >= 16 and n >= 1:
             hi, lo, ld = sp
-            bh, bl, _ = _split_planes(cout, cin, x.device)
-            check(L.pcrcg_split_bf16_dev(weight.data_ptr(), cin, cout, cin, bh.data_ptr(), bl.data_ptr(), ld, _stream()))
+            # the weights' bf16 planes are cached on the weight tensor (version-stamped: an in-place update re-splits them)
+            wsp = _attached(weight, "_pcrcg_wsplit")
+            if wsp is None or wsp[2] != ld or wsp[0].device != x.device:
+                bh, bl, _ = _split_planes(cout, cin, x.device)
+                if bh.shape[1] != ld:
+                    bh = torch.empty((cout, ld), dtype=torch.bfloat16, device=x.device)
+                    bl = torch.empty((cout, ld), dtype=torch.bfloat16, device=x.device)
+                check(L.pcrcg_split_bf16_dev(weight.data_ptr(), cin, cout, cin, bh.data_ptr(), bl.data_ptr(), ld, _stream()))
+                _attach(weight, "_pcrcg_wsplit", (bh, bl, ld))
+            else:
+                bh, bl, _ = wsp
             seg, acc = _stats_begin(n, cout, stat_segments, x.device)
             if acc is not None:
                 check(L.pcrcg_gemm_bf16x3_stats_dev(hi.data_ptr(), lo.data_ptr(), bh.data_ptr(), bl.data_ptr(), ld, out.data_ptr(), cout, n, cout,
@@ -334,14 +343,23 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
     models/blocks.py:456-463 (+ :501, :590, :662, :678).  emit_split: also write the bf16 (hi, lo)
     planes of the result (attached as ``out._pcrcg_split``) for a following :func:`linear`."""
     _need_cuda(x, shortcut)
+    if isinstance(x, PlaneTensor):
+        x = x.dense()
     n, c = x.shape
     mean, rstd, seg = _stats_of(x, segments, eps)
     x = _f32c(x)
     scm = scr = None
+    sc_planes = None
     if shortcut is not None:
-        if shortcut_norm:
-            scm, scr, _ = _stats_of(shortcut, segments, eps)
-        shortcut = _f32c(shortcut)
+        if isinstance(shortcut, PlaneTensor):
+            if shortcut_norm or c % 4 != 0:
+                shortcut = shortcut.dense()
+            else:
+                sc_planes, shortcut = shortcut._pcrcg_split, None
+        if shortcut is not None:
+            if shortcut_norm:
+                scm, scr, _ = _stats_of(shortcut, segments, eps)
+            shortcut = _f32c(shortcut)
     p = lambda t: t.data_ptr() if t is not None else None
     sp = _split_planes(n, c, x.device) if (emit_split and c % 8 == 0 and not _force_simt) else None
     rp = None
@@ -351,10 +369,17 @@ def instance_norm_act(x, segments=None, slope=None, shortcut=None, shortcut_norm
     planes_only = bool(planes_only and sp is not None and c % 64 == 0 and n >= 1 and (rp is not None or not emit_rowpos))
     out = None if planes_only else torch.empty_like(x)
     with torch.cuda.device(x.device):
-        check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
-                                       p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), p(out),
-                                       sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0,
-                                       rp.data_ptr() if rp is not None else None, _stream()))
+        if sc_planes is not None:
+            check(lib().pcrcg_norm_act_planes_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
+                                                  sc_planes[0].data_ptr(), sc_planes[1].data_ptr(), sc_planes[2], None, None,
+                                                  -1.0 if slope is None else float(slope), p(out),
+                                                  sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0,
+                                                  rp.data_ptr() if rp is not None else None, _stream()))
+        else:
+            check(lib().pcrcg_norm_act_dev(x.data_ptr(), n, c, seg.data_ptr(), seg.shape[0] - 1, mean.data_ptr(), rstd.data_ptr(),
+                                           p(shortcut), p(scm), p(scr), -1.0 if slope is None else float(slope), p(out),
+                                           sp[0].data_ptr() if sp else None, sp[1].data_ptr() if sp else None, sp[2] if sp else 0,
+                                           rp.data_ptr() if rp is not None else None, _stream()))
     if planes_only:
         return PlaneTensor(sp[0], sp[1], sp[2], n, c, rp)
     if sp is not None:
@@ -377,8 +402,19 @@ def add_act(x, shortcut, slope):
 
 
 def max_pool(x, inds):
-    """models/blocks.py:86-102"""
+    """models/blocks.py:86-102.  Features held as bf16 planes (:class:`PlaneTensor`) are pooled as planes."""
     _need_cuda(x, inds)
+    if isinstance(x, PlaneTensor):
+        hi, lo, ld = x._pcrcg_split
+        idx, is64, H, stride = _idx(inds)
+        nq, c = idx.shape[0], x.shape[1]
+        if c % 4 == 0:
+            oh, ol, ldo = _split_planes(nq, c, hi.device)
+            with torch.cuda.device(hi.device):
+                check(lib().pcrcg_max_pool_planes_dev(hi.data_ptr(), lo.data_ptr(), x.shape[0], c, ld, idx.data_ptr(), is64, nq, H, stride,
+                                                      oh.data_ptr(), ol.data_ptr(), ldo, _stream()))
+            return PlaneTensor(oh, ol, ldo, nq, c)
+        x = x.dense()
     x = _f32c(x)
     idx, is64, H, stride = _idx(inds)
     nq = idx.shape[0]

@@ -64,6 +64,15 @@ def piped(depth, do_flush):
     return f
 
 
+if os.environ.get("PROBE_SAMPLER"):
+    smp = bench.ClockSampler(0)
+    if os.environ["PROBE_SAMPLER"] == "smi":
+        import pynvml as _p
+        _p.nvmlInit = lambda: (_ for _ in ()).throw(RuntimeError("forced nvidia-smi"))
+    smp.start()
+    time.sleep(0.5)
+    print("sampler mode:", smp.mode, flush=True)
+
 for name, fn in (("sync, flush", sync_loop(True)), ("sync, no flush", sync_loop(False)), ("piped depth 1, flush", piped(1, True)),
                  ("piped depth 2, flush", piped(2, True)), ("piped depth 2, no flush", piped(2, False)), ("piped depth 3, flush", piped(3, True)), ("piped depth 2, flush, after sleep", piped(2, True))):
     for rep in range(2):
