@@ -58,6 +58,10 @@ int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* le
  * Radius search.  queries [nq,3], supports [ns,3] fp32; q_lens / s_lens [nb] int32.
  * Rows: neighbours in ascending (d2, index), global support indices, padded with ns.
  * ------------------------------------------------------------------------------------------- */
+/* Row starts of groups of `group` consecutive clouds (group = 2: fragment pairs = InstanceNorm segments):
+ * out[k] = sum of lens[0 .. k*group), k in [0, nb/group]; *total (device, may be NULL) = sum of all lens. */
+int pcrcg_group_starts_dev(const int32_t* lens, int32_t nb, int32_t group, int32_t* out, int32_t* total, pcrcg_stream_t stream);
+
 size_t pcrcg_radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
 /* Step 1: bin the supports (grid state is kept inside ws). */
 int pcrcg_radius_build_dev(const float* supports, int64_t ns, const int32_t* s_lens, int32_t nb, float radius,
@@ -128,7 +132,8 @@ int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols
                          pcrcg_stream_t stream);
 int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C,
                           int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream);
-/* Same with the column statistics of C accumulated by the epilogue (see pcrcg_kpconv_forward_stats_dev):
+/* Same with the column statistics of C accumulated by the epilogue (see pcrcg_kpconv_forward_stats_dev; stats_acc is
+ * cleared by the call, as in every *_stats_dev entry point):
  * UnaryBlock = Linear -> InstanceNorm (models/blocks.py:497-499) without a statistics pass over C. */
 int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C,
                                 int32_t ldc, int32_t M, int32_t N, int32_t K, const float* row_scale, const int32_t* seg_starts,

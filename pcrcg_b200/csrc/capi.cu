@@ -48,6 +48,7 @@ void prof_end(int slot, cudaStream_t st)
 }
 size_t subsample_ws_bytes(int64_t n, int32_t nb);
 int subsample_batch_dev(const float*, int64_t, const int32_t*, int32_t, float, int32_t, float*, int32_t*, void*, size_t, cudaStream_t);
+int group_starts_dev(const int32_t*, int32_t, int32_t, int32_t*, int32_t*, cudaStream_t);
 size_t radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
 int radius_build_dev(const float*, int64_t, const int32_t*, int32_t, float, void*, size_t, cudaStream_t);
 size_t radius_query_ws_bytes(int64_t nq, int32_t nb);
@@ -185,6 +186,11 @@ int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* le
     return PCRCG_OK;
 }
 
+int pcrcg_group_starts_dev(const int32_t* lens, int32_t nb, int32_t group, int32_t* out, int32_t* total, pcrcg_stream_t stream)
+{
+    return group_starts_dev(lens, nb, group, out, total, (cudaStream_t)stream);
+}
+
 size_t pcrcg_radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb) { return radius_ws_bytes(nq, ns, nb); }
 
 int pcrcg_radius_build_dev(const float* supports, int64_t ns, const int32_t* s_lens, int32_t nb, float radius, void* ws,
@@ -279,6 +285,7 @@ int pcrcg_kpconv_forward_stats_dev(const float* q_pts, int64_t nq, const float* 
                                    float KP_extent, const float* weights, int32_t cout, float* out, void* ws, size_t ws_bytes,
                                    const int32_t* seg_starts, int32_t nseg, double* stats_acc, pcrcg_stream_t stream)
 {
+    if (stats_acc != nullptr && nseg >= 1) PCRCG_CUDA(cudaMemsetAsync(stats_acc, 0, sizeof(double) * 2 * (size_t)nseg * cout, (cudaStream_t)stream));
     return kpconv_forward_dev(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K, KP_extent, weights,
                               cout, out, ws, ws_bytes, (cudaStream_t)stream, x_hi, x_lo, ldxs, row_positive, seg_starts, nseg, stats_acc);
 }
@@ -323,6 +330,7 @@ int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* 
                                 double* stats_acc, pcrcg_stream_t stream)
 {
     ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
+    if (stats_acc != nullptr && nseg >= 1) PCRCG_CUDA(cudaMemsetAsync(stats_acc, 0, sizeof(double) * 2 * (size_t)nseg * N, (cudaStream_t)stream));
     return gemm_tc_core_stats_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream, seg_starts, nseg, stats_acc, 0);
 }
 
@@ -386,6 +394,7 @@ int pcrcg_knn_dev(const float* points, int64_t n, const int32_t* cloud_starts, i
 int pcrcg_edge_max_stats_dev(const float* u, int32_t ldu, const float* v, int32_t ldv, const int32_t* knn, int64_t n, int32_t C, int32_t k,
                              const int32_t* cloud_starts, int32_t nb, float* out, double* stats_acc, pcrcg_stream_t stream)
 {
+    if (stats_acc != nullptr && nb >= 1) PCRCG_CUDA(cudaMemsetAsync(stats_acc, 0, sizeof(double) * 2 * (size_t)nb * C, (cudaStream_t)stream));
     return edge_max_stats_dev(u, ldu, v, ldv, knn, n, C, k, cloud_starts, nb, out, stats_acc, (cudaStream_t)stream);
 }
 

@@ -129,6 +129,53 @@ __global__ void __launch_bounds__(1024) k_cloud_starts(const int32_t* __restrict
     if (t == 0) starts[nb] = (int32_t)carry_s;
 }
 
+// out[k] = sum of lens[0 .. k*group) for k in [0, nb/group], and total = sum of all lens (optional): the row starts of
+// groups of `group` consecutive clouds (group = 2: fragment pairs) -- single block, nb is small
+__global__ void __launch_bounds__(1024) k_group_starts(const int32_t* __restrict__ lens, int nb, int group, int32_t* __restrict__ out,
+                                                       int32_t* __restrict__ total)
+{
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) { carry_s = 0; out[0] = 0; }
+    __syncthreads();
+    const int ng = nb / group;
+    for (int base = 0; base < ng; base += 1024) {
+        const int g = base + t;
+        int32_t v = 0;
+        if (g < ng) for (int k = 0; k < group; k++) v += lens[g * group + k];
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        int32_t woff = 0, tot = 0;
+        for (int k = 0; k < 32; k++) { const int32_t x = warp_tot[k]; if (k < w) woff += x; tot += x; }
+        const int32_t carry = carry_s;
+        if (g < ng) out[g + 1] = carry + woff + inc;
+        __syncthreads();
+        if (t == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (t == 0 && total != nullptr) {
+        int32_t s = carry_s;
+        for (int k = ng * group; k < nb; k++) s += lens[k];
+        *total = s;
+    }
+}
+
+int group_starts_dev(const int32_t* lens, int32_t nb, int32_t group, int32_t* out, int32_t* total, cudaStream_t st)
+{
+    PCRCG_REQUIRE(nb >= 1 && group >= 1 && group <= nb, "group_starts: bad group size");
+    count_launches(1);
+    k_group_starts<<<1, 1024, 0, st>>>(lens, nb, group, out, total);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
 int cloud_starts(const int32_t* lens, int32_t nb, int32_t* starts, cudaStream_t st)
 {
     k_cloud_starts<<<1, 1024, 0, st>>>(lens, nb, starts);

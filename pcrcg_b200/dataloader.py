@@ -115,11 +115,8 @@ def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pai
     # per-pair row starts at every layer
     segs = []
     for l in out["stack_lengths"]:
-        if pairs and l.numel() % 2 == 0 and l.numel() > 0:
-            per_pair = l.view(-1, 2).sum(1)
-        else:
-            per_pair = l.sum().view(1)
-        segs.append(torch.cat([torch.zeros(1, dtype=torch.int32, device=device), per_pair.cumsum(0).to(torch.int32)]))
+        paired = pairs and l.numel() % 2 == 0 and l.numel() > 0
+        segs.append(ops.group_starts(l, 2 if paired else max(1, l.numel())))
     out["pair_segments"] = segs
     if return_counts:
         out["neighbor_counts"] = counts_out

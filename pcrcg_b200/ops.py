@@ -70,7 +70,10 @@ def subsample_batch(points, lens, sampleDl, max_p=0):
         out_lens = torch.empty(nb, dtype=torch.int32, device=points.device)
         check(L.pcrcg_subsample_batch_dev(points.data_ptr(), n, lens.data_ptr(), nb, float(sampleDl), int(max_p),
                                           out.data_ptr(), out_lens.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-        m = int(out_lens.sum().item())
+        tot = torch.empty(1, dtype=torch.int32, device=points.device)
+        gs = torch.empty(nb + 1, dtype=torch.int32, device=points.device)
+        check(L.pcrcg_group_starts_dev(out_lens.data_ptr(), nb, 1, gs.data_ptr(), tot.data_ptr(), _stream()))
+        m = int(tot.item())
     return out[:m], out_lens
 
 
@@ -99,7 +102,7 @@ class RadiusGrid:
         with torch.cuda.device(dev):
             rows = torch.empty((nq, width), dtype=torch.int32, device=dev) if width > 0 else None
             counts = torch.empty(nq, dtype=torch.int32, device=dev) if want_counts else None
-            mx = torch.zeros(1, dtype=torch.int32, device=dev)
+            mx = torch.empty(1, dtype=torch.int32, device=dev)            # cleared by the query call
             rp = rows.data_ptr() if rows is not None else None
             cp = counts.data_ptr() if counts is not None else None
             if _cell_centric:
@@ -165,7 +168,7 @@ def _stats_begin(n, cout, stat_segments, device):
     if stat_segments is False or not _fuse_stats or _force_simt or cout % 16 != 0 or n < 1:
         return None, None
     seg = _seg_starts(n, None if stat_segments is True else stat_segments, device)
-    return seg, torch.zeros((seg.shape[0] - 1, 2, cout), dtype=torch.float64, device=device)
+    return seg, torch.empty((seg.shape[0] - 1, 2, cout), dtype=torch.float64, device=device)      # cleared by the *_stats_dev call
 
 
 def _stats_end(out, seg, acc, eps=1e-5):
@@ -462,6 +465,16 @@ def force_simt_contraction(on):
 # =================================================================================================
 # Bottleneck GNN operators (models/gcn.py, models/architectures.py:528-565)
 # =================================================================================================
+def group_starts(lens, group=1):
+    """lens [B] int32 cuda -> int32 [B // group + 1] row starts of groups of `group` consecutive clouds (device, no sync)."""
+    lens = _i32c(lens)
+    nb = lens.shape[0]
+    out = torch.empty(nb // group + 1, dtype=torch.int32, device=lens.device)
+    with torch.cuda.device(lens.device):
+        check(lib().pcrcg_group_starts_dev(lens.data_ptr(), nb, int(group), out.data_ptr(), None, _stream()))
+    return out
+
+
 def cloud_starts(lens):
     """lens [B] (any int tensor / sequence) -> int32 device-agnostic row starts [B+1] (host computation: B is tiny)."""
     l = torch.as_tensor(lens, dtype=torch.int64).cpu()
@@ -504,7 +517,7 @@ def edge_conv_max(uv, cout, knn_idx, starts, slope=0.2, eps=1e-5):
     starts = _i32c(starts.to(dev))
     nb = starts.shape[0] - 1
     m = torch.empty((n, cout), dtype=torch.float32, device=dev)
-    acc = torch.zeros((nb, 2, cout), dtype=torch.float64, device=dev)
+    acc = torch.empty((nb, 2, cout), dtype=torch.float64, device=dev)          # cleared by pcrcg_edge_max_stats_dev
     with torch.cuda.device(dev):
         check(lib().pcrcg_edge_max_stats_dev(uv.data_ptr(), uv.stride(0), uv.data_ptr() + 4 * cout, uv.stride(0), knn_idx.data_ptr(), n, cout, k,
                                              starts.data_ptr(), nb, m.data_ptr(), acc.data_ptr(), _stream()))
