@@ -32,6 +32,9 @@ os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 import numpy as np  # noqa: E402
 
+# steps in flight in the timed loops: the host submits step i + DEPTH while the GPU works on step i, which rides out host
+# hiccups of up to ~2 step times (shared hosts: gaps of 40-60 ms between submissions were seen with nothing else running)
+DEPTH = 3
 METRIC = "3DMatch pairs/s (subsample+radius search+KPConv fwd)"
 UNIT = "pairs/s"
 
@@ -297,7 +300,11 @@ def algorithmic_work(batch, cfg, limits, enc, views=None):
         C2, Hh, Ww = views[0][0]["feature2d"].shape
         work["projection"] = dict(bytes=12 * N[0] + 4 * Hh * Ww * nv + 4 * N[0] * C2 + 4 * N[0] * (C2 + 1), flops=0)
     work["kpconv_aggregate"] = dict(bytes=agg_b, flops=agg_f)
-    work["gemm"] = dict(bytes=gemm_b + lin_b, flops=gemm_f + lin_f, kpconv_flops=gemm_f, linear_flops=lin_f)
+    # the KPConv [K*Cin] x Cout contraction (tensor pipe) and the unary Linears (HBM: N*Cin read + N*Cout written) are separate
+    # classes; "kpconv" = whole KPConv operators (aggregate + contraction, one- and two-kernel forms together)
+    work["kpconv_contraction"] = dict(bytes=gemm_b, flops=gemm_f)
+    work["linear"] = dict(bytes=lin_b, flops=lin_f)
+    work["kpconv"] = dict(bytes=agg_b + gemm_b, flops=agg_f + gemm_f)
     return work, N
 
 
@@ -323,31 +330,39 @@ def quick_measure(workload, P, K, W, rank, world, dev, flush, dist):
         torch.cuda.synchronize()
     for _ in range(W):
         y, batch = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
-    outs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
+    outs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
     path.run_host(pts_host, lens_host, outs[0], views_e2e)
+    def dsteps(n):
+        hs = []
+        for i in range(n):
+            if i >= DEPTH:
+                hs[i - DEPTH].ready.synchronize()
+                hs[i - DEPTH] = None
+            flush.fill_(0.0)
+            hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
+        return hs[-1].result()
+
+    def hsteps(n):
+        pending = [None] * DEPTH
+        for i in range(n):
+            if pending[i % DEPTH] is not None:
+                pending[i % DEPTH].result()
+            flush.fill_(0.0)
+            pending[i % DEPTH] = path.submit_host(pts_host, lens_host, outs[i % DEPTH], views_e2e)
+        for h in pending:
+            if h is not None:
+                h.result()
+    dsteps(2 * DEPTH + 2)                     # allocator steady state of both loop shapes, untimed
+    hsteps(2 * DEPTH + 2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    hs = []
-    for i in range(K):
-        if i >= 2:
-            hs[i - 2].ready.synchronize()
-        flush.fill_(0.0)
-        hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
-    y, _ = hs[-1].result()
+    y, _ = dsteps(K)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     t0 = time.perf_counter()
-    pending = [None, None]
-    for i in range(K):
-        if pending[i & 1] is not None:
-            pending[i & 1].result()
-        flush.fill_(0.0)
-        pending[i & 1] = path.submit_host(pts_host, lens_host, outs[i & 1], views_e2e)
-    for h in pending:
-        if h is not None:
-            h.result()
+    hsteps(K)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1000.0
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -491,43 +506,79 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clock sampler: started BEFORE the warm-up (NVML initialisation and its first queries stall CUDA calls for 100-300 ms on a
+    # fresh box; they must not fall into a timed region); only the samples inside [t_begin, t_end] are reported
+    sampler = ClockSampler(local_rank)
+    if not os.environ.get("PCRCG_BENCH_NOSAMPLER"):
+        sampler.start()
     y = None
     for _ in range(W):
         y, batch = path.run_device(pts_dev, lens_dev, views_per_cloud=views_dev)
-    out_bufs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for i in range(2):
+    out_bufs = [torch.empty((y.shape[0] + 1024, y.shape[1]), dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
+    for i in range(DEPTH):
         path.run_host(pts_host, lens_host, out_bufs[i], views_e2e)
-    wh = [path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev) for _ in range(2)]     # two steps in flight once (allocator warm-up)
+    wh = [path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev) for _ in range(DEPTH)]     # DEPTH steps in flight once (allocator warm-up)
     wh[-1].result()
     torch.cuda.synchronize()
     work, Nlev = algorithmic_work(batch, cfg, limits, path.encoder, views_dev)
 
+    dbg_t = []
+
+    def device_steps(n):
+        """n pipelined steps with inputs resident in HBM; returns the last (features, batch)"""
+        hs = []
+        for i in range(n):
+            if i >= DEPTH:
+                hs[i - DEPTH].ready.synchronize()         # at most DEPTH steps in flight (bounds memory, as in the e2e loop)
+                hs[i - DEPTH] = None                      # drop its tensors: a kept handle pins ~0.6 GB of the allocator's pool
+            dbg_t.append(time.perf_counter())
+            flush.fill_(0.0)                              # L2 flush between timed iterations
+            # asynchronous submission: the pyramid of step i+1 (and its host-side size read-backs) overlaps the encoder of step i
+            hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
+            if os.environ.get("PCRCG_BENCH_SYNC"):
+                hs[-1].result()
+                torch.cuda.current_stream().synchronize()
+        return hs[-1].result()                            # the encoder stream is in order: the last result ends the region
+
+    def host_steps(n):
+        """n pipelined steps through the public host-buffer API: pinned H2D of the inputs, compute, D2H of the encoder features
+        into pinned buffers (copy stream); every result is waited for before returning"""
+        pending = [None] * DEPTH
+        res = None
+        for i in range(n):
+            if pending[i % DEPTH] is not None:
+                pending[i % DEPTH].result()
+            flush.fill_(0.0)
+            pending[i % DEPTH] = path.submit_host(pts_host, lens_host, out_bufs[i % DEPTH], views_e2e)
+        for h in pending:
+            if h is not None:
+                res, _ = h.result()
+        return res
+
+    # untimed warm-up of BOTH timed loops in their exact shape (DEPTH steps in flight): brings PyTorch's caching allocator to its
+    # steady state -- tensors that cross streams are reusable only after their recorded events, so the first pipelined steps call
+    # cudaMalloc (measured: 24 calls and stalls of 100-300 ms when they fell into the timed region)
+    device_steps(max(W, 2 * DEPTH + 2))
+    host_steps(max(W, 2 * DEPTH + 2))
+    torch.cuda.synchronize()
+
     # ---- device-resident timed region ----------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.1)
     launches0 = L.pcrcg_launch_count()
     barrier()
     t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    hs = []
-    dbg_t = []
-    for i in range(K):
-        if i >= 2:
-            hs[i - 2].ready.synchronize()                 # at most two steps in flight (bounds memory, as in the e2e loop)
-        dbg_t.append(time.perf_counter())
-        flush.fill_(0.0)                                  # L2 flush between timed iterations
-        # asynchronous submission: the pyramid of step i+1 (and its host-side size read-backs) overlaps the encoder of step i
-        hs.append(path.submit_device(pts_dev, lens_dev, views_per_cloud=views_dev))
-    y, batch = hs[-1].result()                            # the encoder stream is in order: the last result ends the region
+    dbg_alloc0 = torch.cuda.memory_stats()["num_device_alloc"]
+    del dbg_t[:]
+    y, batch = device_steps(K)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     if os.environ.get("PCRCG_BENCH_DEBUG"):
         st = torch.cuda.memory_stats()
         print("[debug] host ms between submissions:", [round(1000 * (b - a), 1) for a, b in zip(dbg_t, dbg_t[1:])],
-              "cudaMalloc", st["num_device_alloc"], "cudaFree", st["num_device_free"], "retries", st["num_alloc_retries"], file=sys.stderr)
+              "cudaMalloc in the loop", st["num_device_alloc"] - dbg_alloc0, "cudaFree", st["num_device_free"], file=sys.stderr)
     launches = int(L.pcrcg_launch_count() - launches0)
     # per-class device time: the same K steps once more with the library's event pairs around every kernel class (kept out of
     # the region that defines `value`: ~300 extra event records per step are host work the product path does not do)
@@ -549,15 +600,7 @@ def main():
     # before the clock stops.
     barrier()
     t0 = time.perf_counter()
-    pending = [None, None]
-    for i in range(K):
-        if pending[i & 1] is not None:
-            pending[i & 1].result()
-        flush.fill_(0.0)
-        pending[i & 1] = path.submit_host(pts_host, lens_host, out_bufs[i & 1], views_e2e)
-    for h in pending:
-        if h is not None:
-            out, _ = h.result()
+    out = host_steps(K)
     barrier()
     e2e_s = time.perf_counter() - t0
     t_end = time.perf_counter()
@@ -608,7 +651,8 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         kernels = {}
         agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
-               "kpconv_fused": ["kpconv_fused"], "gemm": ["gemm"], "norm_act": ["norm_act"], "pool": ["pool"], "projection": ["projection"]}
+               "kpconv_fused": ["kpconv_fused"], "kpconv_contraction": ["gemm"], "linear": ["linear"], "norm_act": ["norm_act"],
+               "pool": ["pool"], "projection": ["projection"]}
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, parts in agg.items():
             ms = sum(prof[p][0] for p in parts if p in prof) / K
@@ -619,19 +663,30 @@ def main():
                 if work[name]["flops"]:
                     ent["TFLOP/s"] = round(work[name]["flops"] / ms / 1e9, 3)
             kernels[name] = ent
-        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        # whole KPConv operators: the fused kernel covers aggregate + contraction of its layers, so the three classes are summed
+        kp_ms = sum(kernels[k]["ms_per_step"] for k in ("kpconv_aggregate", "kpconv_fused", "kpconv_contraction"))
+        kernels["kpconv"] = {"ms_per_step": round(kp_ms, 4), "share": round(kp_ms * K / tot_ms, 4),
+                             "GB/s": round(work["kpconv"]["bytes"] / kp_ms / 1e6, 2), "TFLOP/s": round(work["kpconv"]["flops"] / kp_ms / 1e9, 3),
+                             "note": "kpconv_aggregate + kpconv_fused + kpconv_contraction"}
+        single = [k for k in kernels if k != "kpconv"]
+        dom = max(single, key=lambda k: kernels[k]["ms_per_step"])
         traffic = None
         tr_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr_path):
-            traffic = json.load(open(tr_path)).get(dom)
-        if dom == "gemm":
+            tj = json.load(open(tr_path))
+            traffic = tj.get(dom)       # DRAM bytes of the class over ONE step (ncu, same command), like `achieved`'s numerator
+        roof_extra = {"per": "step (all launches of the class)", "algorithmic_bytes": work.get(dom, {}).get("bytes"),
+                      "algorithmic_flops": work.get(dom, {}).get("flops") or None}
+        if dom == "kpconv_contraction":
+            # useful flops; the bf16x3 scheme issues 3 MMAs per useful one, so the tensor pipe is 3x busier than `achieved` says
             ach = kernels[dom].get("TFLOP/s", 0.0)
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "traffic": traffic, "peak_source": peak_src + ", bf16 dense sustained"}
+                    "pipe_frac": 3.0 * ach / tf_peak, "traffic": traffic, "peak_source": peak_src + ", bf16 dense sustained"}
         else:
             ach = kernels[dom].get("GB/s", 0.0)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "peak_source": peak_src}
+        roof.update(roof_extra)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

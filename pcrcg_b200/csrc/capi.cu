@@ -75,6 +75,7 @@ void kpconv_set_agg_pipelined(int);
 void kpconv_set_small_fused(int);
 void kpconv_set_chunk_mb(int);
 void kpconv_set_fused(int);
+void gemm_set_prof_class(int);
 int gemm_tc_core_dev(const void*, const void*, const void*, const void*, int, float*, int, int, int, int, const float*, cudaStream_t);
 int split_bf16_dev(const float*, int, int64_t, int, void*, void*, int, cudaStream_t);
 int colstats_dev(const float*, int64_t, int32_t, const int32_t*, int32_t, float, float*, float*, cudaStream_t);
@@ -130,7 +131,7 @@ uint64_t pcrcg_launch_count(void) { return g_launches; }
 int32_t pcrcg_profile_classes(void) { return PC_COUNT; }
 const char* pcrcg_profile_class_name(int32_t c)
 {
-    static const char* names[PC_COUNT] = { "subsample", "radius_build", "radius_query", "kpconv_aggregate", "gemm", "norm_act", "pool", "projection", "kpconv_fused" };
+    static const char* names[PC_COUNT] = { "subsample", "radius_build", "radius_query", "kpconv_aggregate", "gemm", "norm_act", "pool", "projection", "kpconv_fused", "linear" };
     return (c >= 0 && c < PC_COUNT) ? names[c] : "?";
 }
 // Synchronises the device, sums elapsed ms and scope counts per class, clears the records.
@@ -293,7 +294,10 @@ int pcrcg_kpconv_forward_stats_dev(const float* q_pts, int64_t nq, const float* 
 int pcrcg_gemm_dev(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t b_is_nk, float* C, int32_t ldc, int32_t M, int32_t N,
                    int32_t K, const float* row_scale, pcrcg_stream_t stream)
 {
-    return gemm_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
+    gemm_set_prof_class(PC_LINEAR);
+    const int rc = gemm_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
+    gemm_set_prof_class(PC_GEMM);
+    return rc;
 }
 
 void pcrcg_gemm_force_simt(int32_t on) { gemm_set_force_simt(on); }
@@ -321,7 +325,7 @@ int pcrcg_split_bf16_dev(const float* x, int32_t ldx, int64_t rows, int32_t cols
 int pcrcg_gemm_bf16x3_dev(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int32_t ldk, float* C, int32_t ldc,
                           int32_t M, int32_t N, int32_t K, const float* row_scale, pcrcg_stream_t stream)
 {
-    ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
+    ProfScope prof(PC_LINEAR, (cudaStream_t)stream, 0);
     return gemm_tc_core_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream);
 }
 
@@ -329,7 +333,7 @@ int pcrcg_gemm_bf16x3_stats_dev(const void* a_hi, const void* a_lo, const void* 
                                 int32_t M, int32_t N, int32_t K, const float* row_scale, const int32_t* seg_starts, int32_t nseg,
                                 double* stats_acc, pcrcg_stream_t stream)
 {
-    ProfScope prof(PC_GEMM, (cudaStream_t)stream, 0);
+    ProfScope prof(PC_LINEAR, (cudaStream_t)stream, 0);
     if (stats_acc != nullptr && nseg >= 1) PCRCG_CUDA(cudaMemsetAsync(stats_acc, 0, sizeof(double) * 2 * (size_t)nseg * N, (cudaStream_t)stream));
     return gemm_tc_core_stats_dev(a_hi, a_lo, b_hi, b_lo, ldk, C, ldc, M, N, K, row_scale, (cudaStream_t)stream, seg_starts, nseg, stats_acc, 0);
 }

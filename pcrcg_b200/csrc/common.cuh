@@ -44,7 +44,7 @@ constexpr int kNumSMs = 148;   // B200
 // ---- per-kernel-class device timing (CUDA events on the launching stream) + launch counter ------
 // Enabled by pcrcg_profile_enable(1); a ProfScope records an event pair around the launches of one
 // kernel class; pcrcg_profile_report() synchronises and sums elapsed times per class.
-enum ProfClass { PC_SUBSAMPLE = 0, PC_RADIUS_BUILD, PC_RADIUS_QUERY, PC_KPCONV_AGG, PC_GEMM, PC_NORM, PC_POOL, PC_PROJECT, PC_KPCONV_FUSED, PC_COUNT };
+enum ProfClass { PC_SUBSAMPLE = 0, PC_RADIUS_BUILD, PC_RADIUS_QUERY, PC_KPCONV_AGG, PC_GEMM, PC_NORM, PC_POOL, PC_PROJECT, PC_KPCONV_FUSED, PC_LINEAR, PC_COUNT };
 void prof_begin(int cls, cudaStream_t st, int* slot);
 void prof_end(int slot, cudaStream_t st);
 void count_launches(int n);

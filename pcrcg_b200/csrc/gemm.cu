@@ -86,13 +86,17 @@ int gemm_tc_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, f
 static int g_force_simt = 0;
 void gemm_set_force_simt(int v) { g_force_simt = v; }
 int gemm_force_simt_get() { return g_force_simt; }
+// profile class of gemm_dev's launches: the KPConv weight contraction (PC_GEMM, the callers inside kpconv.cu) or a unary
+// Linear / any other dense product entered through the C ABI (PC_LINEAR, set by capi.cu around the call)
+static int g_gemm_prof_class = PC_GEMM;
+void gemm_set_prof_class(int c) { g_gemm_prof_class = c; }
 
 int gemm_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, float* C, int ldc, int M, int N, int K,
              const float* row_scale, cudaStream_t st)
 {
     if (M <= 0 || N <= 0) return PCRCG_OK;
     PCRCG_REQUIRE(K >= 1, "gemm: K must be >= 1");
-    ProfScope prof(PC_GEMM, st, 1);
+    ProfScope prof(g_gemm_prof_class, st, 1);
     if (!g_force_simt) {
         bool handled = false;
         PCRCG_TRY(gemm_tc_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, st, &handled));

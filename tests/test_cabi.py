@@ -32,7 +32,7 @@ def test_binding_table_matches_header():
     L = _lib.lib()
     assert L.pcrcg_version() >= 100
     assert L.pcrcg_subsample_ws_bytes(1000, 2) > 0 and L.pcrcg_radius_ws_bytes(1000, 1000, 2) > 0
-    assert L.pcrcg_profile_classes() >= 9 and L.pcrcg_profile_class_name(8) == b"kpconv_fused" and L.pcrcg_profile_class_name(4) == b"gemm"
+    assert L.pcrcg_profile_classes() >= 10 and L.pcrcg_profile_class_name(8) == b"kpconv_fused" and L.pcrcg_profile_class_name(9) == b"linear" and L.pcrcg_profile_class_name(4) == b"gemm"
 
 
 def test_no_oracle_in_product_path():

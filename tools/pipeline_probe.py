@@ -56,6 +56,7 @@ def piped(depth, do_flush):
         for i in range(K):
             if i >= depth:
                 hs[i - depth].ready.synchronize()
+                hs[i - depth] = None
             STAMPS.append(time.perf_counter())
             if do_flush:
                 flush.fill_(0.0)

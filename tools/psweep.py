@@ -40,6 +40,7 @@ for P in (1, 4, 16, 32, 64):
     for i in range(K):
         if i >= 2:
             hs[i - 2].ready.synchronize()
+            hs[i - 2] = None
         hs.append(path.submit_device(pts, lens))
     hs[-1].result()
     torch.cuda.synchronize()
