@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
         const uint32_t dst_off = (uint32_t)(plane * ABP_ROWS * AB_PITCH + chunk * 16 + rsel * AB_PITCH);
         const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
 
-        // Points are CLAIMED from a per-CTA counter (sequence number m -> row m % 8 of tile m / 8), three per warp in flight
-        // (current, next: indices and query loaded, after next: indices requested).  A static round-robin lets the warps
+        // Points are CLAIMED from a per-CTA counter (sequence number m -> row m % 8 of tile m / 8), four per warp in flight
+        // (current, next: indices and query loaded, after next: indices requested, one more: claim in flight).  A static round-robin lets the warps
         // drift apart until the fast ones sit at the edge of the 3-tile ring all the time (measured: 14 % of the producer
         // cycles in the slot wait); claimed in order, the points being finished stay within ~2 tiles of each other.
         const int m_end = my_tiles * FZ_TILE;
@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
 
         int m = claim();
         int nm = claim();
+        int fm_next = claim();                      // claimed one iteration before it is used: hides the shared-memory atomic
         (void)pw;
         if (m < m_end) {
             int j0, j1;
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
             IdxT nr0, nr1;
             load_raw(nm, nr0, nr1);
             while (m < m_end) {
-                const int fm = claim();
+                const int fm = fm_next;
+                fm_next = claim();
                 IdxT fr0, fr1;
                 load_raw(fm, fr0, fr1);
                 int nj0 = ns, nj1 = ns;
