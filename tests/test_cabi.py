@@ -61,3 +61,21 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA tensors required"):
         ops.kpconv_forward(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 2, dtype=torch.int64), torch.zeros(4, 1),
                            torch.zeros(15, 3), torch.zeros(15, 1, 8), 0.05)
+
+
+def test_features_and_classes_are_refused_loudly():
+    """the feature / label outputs of the reference's subsample_batch are outside the hot path; the
+    drop-in refuses them instead of silently returning two arrays less (no GPU needed: the check precedes every device call)"""
+    import numpy as np
+    from pcrcg_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as cpp_subsampling
+    from pcrcg_b200 import dataloader
+    pts = np.zeros((4, 3), np.float32)
+    for kw in (dict(features=np.ones((4, 2), np.float32)), dict(classes=np.zeros((4, 1), np.int32))):
+        with pytest.raises(NotImplementedError, match="outside the KPConv hot path"):
+            cpp_subsampling.subsample_batch(pts, [4], sampleDl=0.1, **kw)
+        with pytest.raises(NotImplementedError, match="outside the KPConv hot path"):
+            cpp_subsampling.subsample(pts, sampleDl=0.1, **kw)
+    with pytest.raises(NotImplementedError):
+        dataloader.batch_grid_subsampling_kpconv(pts, [4], features=np.ones((4, 2), np.float32))
+    with pytest.raises(RuntimeError, match="Error parsing method"):
+        cpp_subsampling.subsample_batch(pts, [4], method="nonsense")
