@@ -79,6 +79,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
     const uint32_t tmem_slot = bar_base + 8u * (2 * FZ_SLOTS + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
     int* next_point = reinterpret_cast<int*>(base_ptr + (tmem_slot + 8u - base));      // next unclaimed point of this CTA's sequence
+    // Number of tiles whose MMAs have been ISSUED (written by the MMA thread after its commits, read by the producers).  A
+    // producer may test the parity of a slot's "empty" barrier for tile i only once tile i - 3 (the slot's previous use) has been
+    // issued: then every earlier commit on that barrier has completed (tile i - 3 could only be filled after the commit of tile
+    // i - 6), the barrier is at most ONE completion behind and the parity test is unambiguous.  Without this gate a warp that
+    // has drifted two uses of a slot ahead (13 warps x 3 claims in flight = 39 points = up to 6 tiles; a 4-k-step point next to
+    // 1-k-step points is enough) sees the parity of tile i - 6's completion, overwrites a tile that is still being filled and
+    // adds arrivals to its barrier: wrong rows or a hang (seen once in a 4-GPU run of round 2; tests/test_fused_protocol.py
+    // reproduces it in a model of these barriers and shows that the gate removes it).
+    const uint32_t tiles_issued = tmem_slot + 12u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (nq + FZ_TILE - 1) / FZ_TILE;
@@ -88,6 +97,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
     if (warp == FZ_FIRST_PW - 1) {
         if (lane == 0) {
             *next_point = 0;
+            sts_release(tiles_issued, 0);
             for (int s = 0; s < FZ_SLOTS; s++) { mbar_init(full_bar(s), FZ_TILE); mbar_init(empty_bar(s), 1); }
             for (int a = 0; a < 2; a++) { mbar_init(accfull_bar(a), 1); mbar_init(accempty_bar(a), 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,8 +150,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
         const uint32_t dst_off = (uint32_t)(plane * ABP_ROWS * AB_PITCH + chunk * 16 + rsel * AB_PITCH);
         const uint32_t lm_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * AB_PITCH + (uint32_t)(lane >> 4) * 16;
 
-        // Points are CLAIMED from a per-CTA counter (sequence number m -> row m % 8 of tile m / 8), four per warp in flight
-        // (current, next: indices and query loaded, after next: indices requested, one more: claim in flight).  A static round-robin lets the warps
+        // Points are CLAIMED from a per-CTA counter (sequence number m -> row m % 8 of tile m / 8), three per warp in flight
+        // (current, next: indices and query loaded, after next: indices requested).  A static round-robin lets the warps
         // drift apart until the fast ones sit at the edge of the 3-tile ring all the time (measured: 14 % of the producer
         // cycles in the slot wait); claimed in order, the points being finished stay within ~2 tiles of each other.
         const int m_end = my_tiles * FZ_TILE;
@@ -232,7 +242,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
         // (t and 4+t) per plane and kernel point; odd g stores chunk 4+t first, so the 8 lanes of a store phase hit 8 chunks.
         auto store_point = [&](int m, float inv) {
             const int i = m >> 3, row = m & 7, slot = i % FZ_SLOTS;
-            mbar_wait(empty_bar(slot), (uint32_t)(((i / FZ_SLOTS) & 1) ^ 1));       // the MMAs of the slot's previous tile are done
+            if (i >= FZ_SLOTS && lds_acquire(tiles_issued) < i - (FZ_SLOTS - 1)) {   // the slot's previous tile (i - 3) has been issued
+                const long long t0 = clock64();
+                while (lds_acquire(tiles_issued) < i - (FZ_SLOTS - 1)) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > kSpinLimitCycles) __trap();
+                }
+            }
+            mbar_wait(empty_bar(slot), (uint32_t)(((i / FZ_SLOTS) & 1) ^ 1));       // ... and its MMAs are done
             if (point_of(m) < nq) {
                 const uint32_t rbase = base + (uint32_t)(slot * FZ_SLOT_BYTES + row * 128);
 #pragma unroll
@@ -267,7 +284,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
 
         int m = claim();
         int nm = claim();
-        int fm_next = claim();                      // claimed one iteration before it is used: hides the shared-memory atomic
         (void)pw;
         if (m < m_end) {
             int j0, j1;
@@ -293,8 +309,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
             IdxT nr0, nr1;
             load_raw(nm, nr0, nr1);
             while (m < m_end) {
-                const int fm = fm_next;
-                fm_next = claim();
+                const int fm = claim();
                 IdxT fr0, fr1;
                 load_raw(fm, fr0, fr1);
                 int nj0 = ns, nj1 = ns;
@@ -375,6 +390,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
                 }
                 umma_commit(empty_bar(slot));
                 umma_commit(accfull_bar(acc));
+                sts_release(tiles_issued, i + 1);
             }
         }
     } else {

@@ -1,0 +1,227 @@
+"""Host-side model of the fused KPConv's tile ring (pcrcg_b200/csrc/kpconv_fused.cu): 13 producer warps that CLAIM points from a
+per-CTA counter and fill 8-point tiles in a 3-slot shared-memory ring, one MMA thread, 4 epilogue warps, all synchronised by
+phase-parity mbarriers.  No GPU: the model restates the kernel's waits, arrivals and parities one for one and runs them under
+randomised and adversarial timings (a discrete-event simulation), checking that
+
+  * no producer ever writes into a slot whose previous tile has not been consumed by the MMAs,
+  * the MMA thread always reads exactly the 8 rows of the tile it expects,
+  * every barrier phase receives exactly its arrival count, and nothing deadlocks.
+
+It documents a defect found in round 2: WITHOUT the "tiles_issued" gate a warp that runs two uses of a slot ahead passes the
+parity test of the slot's "empty" barrier on the completion of tile i - 6 (parity waits cannot tell phase c from phase c + 2),
+overwrites tile i - 3 and adds arrivals to its barrier -> wrong rows or a hang (one 4-GPU bench run hung).  The test shows the
+un-gated protocol failing in the model and the gated one (the kernel as shipped) surviving the same schedules."""
+import heapq
+import random
+
+import pytest
+
+SLOTS, TILE, ACCS = 3, 8, 2
+
+
+class Violation(Exception):
+    pass
+
+
+class MBar:
+    """mbarrier restricted to what the kernel uses: init(count), arrive, try_wait.parity"""
+
+    def __init__(self, count):
+        self.count, self.pending, self.completed = count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        if self.pending == 0:
+            self.completed += 1
+            self.pending = self.count
+
+    def test(self, parity):
+        # try_wait.parity(P): true once the phase of parity P is over = the phase in progress has the other parity
+        return (self.completed & 1) != parity
+
+
+class Sim:
+    def __init__(self, ntiles, warps, claims_in_flight, gate, seed, point_time, mma_time=0.05, epi_time=0.05):
+        self.ntiles, self.warps, self.cif, self.gate = ntiles, warps, claims_in_flight, gate
+        self.rng = random.Random(seed)
+        self.point_time, self.mma_time, self.epi_time = point_time, mma_time, epi_time
+        self.full = [MBar(TILE) for _ in range(SLOTS)]
+        self.empty = [MBar(1) for _ in range(SLOTS)]
+        self.accfull = [MBar(1) for _ in range(ACCS)]
+        self.accempty = [MBar(4) for _ in range(ACCS)]
+        self.next_point = 0
+        self.tiles_issued = 0
+        self.slot_rows = [dict() for _ in range(SLOTS)]        # row -> tile that wrote it (since the slot's last consumption)
+        self.consumed = [False] * ntiles                        # the MMAs of the tile have completed (its commit has arrived)
+        self.epilogued = 0
+        self.now = 0.0
+        self.heap, self.seq, self.waiting = [], 0, []
+
+    # ---- scheduler ---------------------------------------------------------------------------------
+    def spawn(self, gen):
+        self._advance(gen)
+
+    def _advance(self, gen):
+        try:
+            req = next(gen)
+        except StopIteration:
+            return
+        if req[0] == "sleep":
+            self.seq += 1
+            heapq.heappush(self.heap, (self.now + req[1], self.seq, gen))
+        else:                                   # ("wait", predicate)
+            if req[1]():
+                self._advance(gen)
+            else:
+                self.waiting.append((req[1], gen))
+
+    def at(self, dt, fn):
+        def g():
+            yield ("sleep", dt)
+            fn()
+        self.spawn(g())
+
+    def run(self):
+        while self.heap:
+            self.now, _, gen = heapq.heappop(self.heap)
+            self._advance(gen)
+            progress = True
+            while progress:                     # wake every waiter whose predicate became true
+                progress = False
+                for k, (pred, g) in enumerate(self.waiting):
+                    if pred():
+                        del self.waiting[k]
+                        self._advance(g)
+                        progress = True
+                        break
+        if self.waiting or self.epilogued != self.ntiles:
+            raise Violation(f"deadlock: {len(self.waiting)} actors blocked, {self.epilogued}/{self.ntiles} tiles finished")
+
+    # ---- actors (each line mirrors a line of the kernel) ------------------------------------------------
+    def claim(self):
+        v = self.next_point
+        self.next_point += 1
+        return v
+
+    def producer(self, w):
+        m_end = self.ntiles * TILE
+        q = []
+        for _ in range(self.cif - 1):                            # m, nm (, fm_next): claims taken before the loop; the warps start
+            q.append(self.claim())                               # together, so these interleave (warp w gets w, w + 13, ...)
+            yield ("sleep", 0.0)
+        while q[0] < m_end:
+            q.append(self.claim())                               # fm (or the claim one further ahead)
+            m = q.pop(0)
+            yield ("sleep", self.point_time(self.rng, w, m))     # gather + influence + mma.sync of point m
+            i, row = divmod(m, TILE)
+            slot, use = i % SLOTS, i // SLOTS
+            if self.gate:                                        # while (tiles_issued < i - (SLOTS - 1)) ...
+                yield ("wait", lambda i=i: self.tiles_issued >= i - (SLOTS - 1))
+            yield ("wait", lambda slot=slot, use=use: self.empty[slot].test((use & 1) ^ 1))
+            if i >= SLOTS and not self.consumed[i - SLOTS]:
+                raise Violation(f"warp {w} writes row {row} of tile {i} into slot {slot} before tile {i - SLOTS} was consumed "
+                                f"(barrier completions {self.empty[slot].completed}, expected {use})")
+            self.slot_rows[slot][row] = i
+            self.full[slot].arrive()
+
+    def mma(self):
+        for i in range(self.ntiles):
+            slot, acc = i % SLOTS, i % ACCS
+            yield ("wait", lambda acc=acc, i=i: self.accempty[acc].test((((i // ACCS) & 1)) ^ 1))
+            yield ("wait", lambda slot=slot, i=i: self.full[slot].test((i // SLOTS) & 1))
+            rows = self.slot_rows[slot]
+            if sorted(rows) != list(range(TILE)) or any(t != i for t in rows.values()):
+                raise Violation(f"MMA of tile {i} reads slot {slot} holding {rows}")
+
+            def done(i=i, slot=slot, acc=acc):                   # tcgen05.commit x2: arrive when the MMAs have completed
+                self.consumed[i] = True
+                self.slot_rows[slot] = dict()
+                self.empty[slot].arrive()
+                self.accfull[acc].arrive()
+            self.at(self.mma_time * (0.5 + self.rng.random()), done)
+            self.tiles_issued = i + 1
+            yield ("sleep", 0.01)
+
+    def epilogue(self, q):
+        for i in range(self.ntiles):
+            acc = i % ACCS
+            yield ("wait", lambda acc=acc, i=i: self.accfull[acc].test((i // ACCS) & 1))
+            yield ("sleep", self.epi_time * (0.5 + self.rng.random()))
+            self.accempty[acc].arrive()
+            if q == 0:
+                self.epilogued += 1
+
+    def go(self):
+        for w in range(self.warps):
+            self.spawn(self.producer(w))
+        self.spawn(self.mma())
+        for q in range(4):
+            self.spawn(self.epilogue(q))
+        self.run()
+        for b in self.full + self.empty + self.accfull + self.accempty:
+            assert b.pending == b.count, "a barrier phase was left with stray arrivals"
+
+
+def heavy_tail(rng, w, m):
+    """1-4 k-steps per point (neighbour lists of 1..64 entries in 16-neighbour steps) and an occasional long memory stall"""
+    t = rng.choice((1, 1, 2, 3, 4)) * (0.8 + 0.4 * rng.random())
+    if rng.random() < 0.03:
+        t *= rng.choice((5, 10, 20))
+    return t
+
+
+def straggler(rng, w, m):
+    """one warp stalls for a long time on an early point, another is slow for a while and then fast"""
+    if m == 5:
+        return 400.0
+    if w == 7 and m < 40:
+        return 25.0
+    return 1.0
+
+
+def run(gate, cif, seed, point_time=heavy_tail, ntiles=48, warps=13):
+    Sim(ntiles, warps, cif, gate, seed, point_time).go()
+
+
+def test_parity_wait_cannot_tell_two_phases_apart():
+    b = MBar(1)
+    want_use = 2                                   # a producer about to fill the slot's THIRD tile waits for the second completion
+    assert b.test((want_use & 1) ^ 1), "on a barrier with 0 completions the wait for completion 2 passes at once: the ambiguity"
+    b.arrive()
+    assert not b.test((want_use & 1) ^ 1), "one completion behind: the parity wait blocks as intended"
+    b.arrive()
+    assert b.test((want_use & 1) ^ 1)
+
+
+@pytest.mark.parametrize("cif", [3, 4])
+def test_ungated_ring_fails_under_drift(cif):
+    """The protocol as it was before the gate (3 claims per warp in flight; 4 with the claim issued one iteration ahead)."""
+    failures = 0
+    for seed in range(300):
+        try:
+            run(False, cif, seed)
+        except Violation:
+            failures += 1
+    assert failures > 0, "the model no longer reproduces the round-2 defect: is it still the kernel's protocol?"
+    # nearly uniform point times (what the kernel sees most of the time: 3 k-steps per point) do not trigger it, which is why
+    # the GPU parity tests and a few hundred bench steps had passed before a run hung
+    for seed in range(50):
+        run(False, cif, seed, point_time=lambda rng, w, m: 3.0 * (0.9 + 0.2 * rng.random()))
+
+
+@pytest.mark.parametrize("cif", [3, 4])
+def test_gated_ring_is_safe(cif):
+    """The kernel as shipped (cif = 3); the gate also makes the deeper claim pipeline (cif = 4) safe."""
+    for seed in range(1500):
+        run(True, cif, seed)
+    run(True, cif, 0, point_time=straggler)
+    for seed in range(200):                       # extremes: everything instantaneous but one warp / a single warp / tiny grids
+        run(True, cif, seed, point_time=lambda rng, w, m: 0.0 if w else 50.0 * rng.random())
+        run(True, cif, seed, ntiles=1 + seed % 7, warps=1 + seed % 13)
+
+
+def test_gated_ring_tail_tiles():
+    """my_tiles = 0, 1, 2 (fewer tiles than slots) and claims past the end"""
+    for nt in (0, 1, 2, 3, 4):
+        for seed in range(50):
+            run(True, 3, seed, ntiles=nt)
