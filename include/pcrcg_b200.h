@@ -54,6 +54,25 @@ int pcrcg_subsample_batch_dev(const float* points, int64_t n, const int32_t* len
 int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* lens, int32_t nb, float sampleDl,
                                int32_t max_p, float** out_points, int64_t* out_m, int32_t* out_lens);
 
+/* The same with per-point features [n,fdim] fp32 and / or integer classes [n,ldim] (either may be NULL; its dim is then
+ * ignored): zip!cpp_subsampling/wrapper.cpp:62-333 subsample_batch(points, batches, features=, classes=, ...) ->
+ * zip!cpp_subsampling/grid_subsampling/grid_subsampling.cpp:34-102.  Feature rows are the fp32 sums in point order divided by
+ * (float)count; a class is the first maximal vote in the iteration order of libstdc++'s unordered_map<int,int>
+ * (csrc/label_vote.h).  Not on the KPConv pyramid's path (datasets/dataloader.py:289 passes neither).
+ * ldim > 1 needs nb == 1 (grid_subsampling.cpp:157-158 mis-slices the classes of later clouds: no reference behaviour).
+ * out_features [n,fdim], out_classes [n,ldim]: upper bounds like out_points.  status: device int32, required with classes,
+ * set to 1 if a voxel held more than 64 distinct labels in one column (its vote is then unreliable); read it after
+ * synchronising.  The _host form checks it and fails. */
+size_t pcrcg_subsample_ex_ws_bytes(int64_t n, int32_t nb, int32_t fdim, int32_t ldim);
+int pcrcg_subsample_batch_ex_dev(const float* points, int64_t n, const int32_t* lens, int32_t nb, float sampleDl, int32_t max_p,
+                                 const float* features, int32_t fdim, const int32_t* classes, int32_t ldim, float* out_points,
+                                 int32_t* out_lens, float* out_features, int32_t* out_classes, int32_t* status, void* ws,
+                                 size_t ws_bytes, pcrcg_stream_t stream);
+/* *out_features ([*out_m,fdim]) / *out_classes ([*out_m,ldim]) are malloc'ed like *out_points (pcrcg_free). */
+int pcrcg_subsample_batch_ex_host(const float* points, int64_t n, const int32_t* lens, int32_t nb, float sampleDl, int32_t max_p,
+                                  const float* features, int32_t fdim, const int32_t* classes, int32_t ldim, float** out_points,
+                                  int64_t* out_m, int32_t* out_lens, float** out_features, int32_t** out_classes);
+
 /* ---------------------------------------------------------------------------------------------
  * Radius search.  queries [nq,3], supports [ns,3] fp32; q_lens / s_lens [nb] int32.
  * Rows: neighbours in ascending (d2, index), global support indices, padded with ns.

@@ -46,6 +46,32 @@ def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32)).reshape(-1)
 
 
+def _subsample_ex(fn, has_cap, points, batches, features, classes, sampleDl, max_p):
+    p, b = _f32(points, 3), _i32(batches)
+    n1 = max(len(p), 1)
+    f = None if features is None else _f32(features)
+    c = None if classes is None else np.ascontiguousarray(np.asarray(classes, dtype=np.int32))
+    fdim = 0 if f is None else f.shape[1]
+    if c is not None and c.ndim == 1:
+        c = c.reshape(-1, 1)
+    ldim = 1 if c is None else c.shape[1]
+    out, ol = np.empty((n1, 3), np.float32), np.empty(len(b), np.int32)
+    of = np.empty((n1, max(fdim, 1)), np.float32)
+    oc = np.empty((n1, ldim), np.int32)
+    args = [p, len(p), b, len(b), sampleDl, max_p, None if f is None else f.ctypes.data, fdim, None if c is None else c.ctypes.data, ldim, out]
+    args += ([len(out)] if has_cap else []) + [ol, of.ctypes.data, oc.ctypes.data]
+    m = fn(*args)
+    if m == -2:
+        raise ValueError("classes with more than one column and more than one cloud: undefined in the reference (grid_subsampling.cpp:157-158)")
+    assert m >= 0
+    res = [out[:m].copy(), ol]
+    if f is not None:
+        res.append(of[:m, :fdim].copy())
+    if c is not None:
+        res.append(oc[:m].copy())
+    return tuple(res)
+
+
 # ------------------------------------------------------------------------------------------------
 class _Port:
     def __init__(self):
@@ -54,6 +80,11 @@ class _Port:
         L = C.CDLL(_PORT_SO)
         L.oracle_subsample_batch.restype = C.c_int64
         L.oracle_subsample_batch.argtypes = [_f32p, C.c_int64, _i32p, C.c_int32, C.c_float, C.c_int32, _f32p, _i32p]
+        L.oracle_subsample_batch_ex.restype = C.c_int64
+        L.oracle_subsample_batch_ex.argtypes = [_f32p, C.c_int64, _i32p, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_int32, _f32p, _i32p, C.c_void_p, C.c_void_p]
+        L.oracle_label_vote.restype = C.c_int32
+        L.oracle_label_vote.argtypes = [_i32p, C.c_int64]
         L.oracle_voxel_keys.restype = None
         L.oracle_voxel_keys.argtypes = [_f32p, C.c_int64, C.c_float, _u64p, _f32p, _u64p]
         L.oracle_radius_count.restype = C.c_int32
@@ -73,6 +104,14 @@ class _Port:
         ol = np.empty(len(b), np.int32)
         m = self.L.oracle_subsample_batch(p, len(p), b, len(b), sampleDl, max_p, out, ol)
         return out[:m].copy(), ol
+
+    # grid_subsampling.cpp:109-211 with features and / or classes -> (points, lens[, features][, classes]) like wrapper.cpp:318-326
+    def subsample_batch_ex(self, points, batches, features=None, classes=None, sampleDl=0.1, max_p=0):
+        return _subsample_ex(self.L.oracle_subsample_batch_ex, False, points, batches, features, classes, sampleDl, max_p)
+
+    def label_vote(self, labels):
+        l = _i32(labels)
+        return int(self.L.oracle_label_vote(l, len(l)))
 
     def voxel_keys(self, points, sampleDl):
         p = _f32(points, 3)
@@ -116,6 +155,11 @@ class _Ref:
         L = C.CDLL(_REF_SO)
         L.ref_subsample_batch.restype = C.c_long
         L.ref_subsample_batch.argtypes = [_f32p, C.c_long, _i32p, C.c_int, C.c_float, C.c_int, _f32p, C.c_long, _i32p]
+        L.ref_subsample_batch_ex.restype = C.c_long
+        L.ref_subsample_batch_ex.argtypes = [_f32p, C.c_long, _i32p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                             _f32p, C.c_long, _i32p, C.c_void_p, C.c_void_p]
+        L.ref_label_vote.restype = C.c_int
+        L.ref_label_vote.argtypes = [_i32p, C.c_long]
         L.ref_batch_query.restype = C.c_long
         L.ref_batch_query.argtypes = [_f32p, C.c_long, _f32p, C.c_long, _i32p, _i32p, C.c_int, C.c_float]
         L.ref_batch_query_fetch.restype = None
@@ -131,6 +175,13 @@ class _Ref:
         m = self.L.ref_subsample_batch(p, len(p), b, len(b), sampleDl, max_p, out, len(out), ol)
         assert m >= 0
         return out[:m].copy(), ol
+
+    def subsample_batch_ex(self, points, batches, features=None, classes=None, sampleDl=0.1, max_p=0):
+        return _subsample_ex(self.L.ref_subsample_batch_ex, True, points, batches, features, classes, sampleDl, max_p)
+
+    def label_vote(self, labels):
+        l = _i32(labels)
+        return int(self.L.ref_label_vote(l, len(l)))
 
     def batch_query(self, queries, supports, q_batches, s_batches, radius):
         """Raw reference output [Nq, max_count] (tie order = kd-tree traversal + unstable sort)."""

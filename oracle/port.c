@@ -12,6 +12,7 @@
  *   zip!cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106   grid_subsampling
  *   zip!cpp_subsampling/grid_subsampling/grid_subsampling.cpp:109-211 batch_grid_subsampling
  *   zip!cpp_subsampling/grid_subsampling/grid_subsampling.h:74-79     SampledData::update_points
+ *   zip!cpp_subsampling/grid_subsampling/grid_subsampling.h:42-73     SampledData::update_all / _features / _classes
  *   zip!cpp_utils/cloud/cloud.cpp:27-66                               min_point / max_point
  *   cpp_wrappers/cpp_neighbors/neighbors/neighbors.cpp:211-332        batch_nanoflann_neighbors
  *   zip!cpp_utils/nanoflann/nanoflann.hpp:432-440 (L2_Simple_Adaptor), :250 (strict d2 < r2),
@@ -129,8 +130,57 @@ static int64_t um_find(const umap_t* m, uint64_t k)
  * (never expected) negative cell index wraps modulo 2^64.  Kept for bit-parity of the key. */
 static uint64_t to_size_t(float f) { return (uint64_t)(int64_t)f; }
 
-/* One cloud: grid_subsampling.cpp:5-106 (points only).  out must hold 3*n floats.  Returns M. */
-static int64_t subsample_one(const float* p, int64_t n, float dl, float* out)
+/* Votes of one voxel and one label column: (label, count) in order of first occurrence -- the unordered_map<int,int> of
+ * grid_subsampling.h:22 as far as its CONTENT goes; its iteration order is rebuilt at output time (label_vote_pick). */
+typedef struct { int32_t* lab; int32_t* cnt; int32_t D, cap; } votes_t;
+
+static void votes_add(votes_t* v, int32_t label)            /* grid_subsampling.h:56-61  labels[i][*it] += 1 */
+{
+    for (int32_t e = 0; e < v->D; e++)
+        if (v->lab[e] == label) { v->cnt[e]++; return; }
+    if (v->D == v->cap) {
+        v->cap = v->cap ? 2 * v->cap : 4;
+        v->lab = (int32_t*)realloc(v->lab, sizeof(int32_t) * (size_t)v->cap);
+        v->cnt = (int32_t*)realloc(v->cnt, sizeof(int32_t) * (size_t)v->cap);
+    }
+    v->lab[v->D] = label;
+    v->cnt[v->D] = 1;
+    v->D++;
+}
+
+/* grid_subsampling.cpp:100-101: max_element over the map = the FIRST maximal count in iteration order.  The order is obtained
+ * by inserting the distinct labels, in order of first occurrence, into the literal container model above
+ * (std::hash<int> is the identity: key = (size_t)label). */
+static int32_t label_vote_pick(const votes_t* v)
+{
+    umap_t m;
+    int64_t D = v->D;
+    m.next = (int64_t*)malloc(sizeof(int64_t) * (size_t)D);
+    m.key = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)D);
+    m.bucket = (int64_t*)malloc(sizeof(int64_t));
+    m.bucket[0] = UM_NONE;
+    m.nbkt = 1; m.head = UM_NONE; m.size = 0; m.sched = 0; m.next_resize = 0;
+    for (int64_t e = 0; e < D; e++) {
+        if ((uint64_t)m.size + 1 > m.next_resize && m.sched < N_SCHEDULE) {
+            um_rehash(&m, k_bucket_schedule[m.sched++]);
+            m.next_resize = m.nbkt;
+        }
+        int64_t node = m.size++;
+        m.key[node] = (uint64_t)(int64_t)v->lab[e];
+        um_insert_bucket_begin(&m, m.key[node] % m.nbkt, node);
+    }
+    int64_t best = m.head;
+    for (int64_t q = m.head; q != UM_NONE; q = m.next[q])
+        if (v->cnt[best] < v->cnt[q]) best = q;
+    int32_t r = v->lab[best];
+    free(m.next); free(m.key); free(m.bucket);
+    return r;
+}
+
+/* One cloud: grid_subsampling.cpp:5-106.  out must hold 3*n floats.  Optional per-point features f [n, fdim] -> of [M, fdim]
+ * (sums in point order divided by (float)count, :88-96) and classes c [n, ldim] -> oc [M, ldim] (:97-102).  Returns M. */
+static int64_t subsample_one(const float* p, int64_t n, float dl, float* out, const float* f, int32_t fdim, float* of,
+                             const int32_t* c, int32_t ldim, int32_t* oc)
 {
     if (n <= 0) return 0;
     /* cloud.cpp:27-66 */
@@ -157,6 +207,8 @@ static int64_t subsample_one(const float* p, int64_t n, float dl, float* out)
     m.nbkt = 1; m.head = UM_NONE; m.size = 0; m.sched = 0; m.next_resize = 0;
     float* sum = (float*)calloc((size_t)n * 3, sizeof(float));
     int* cnt = (int*)calloc((size_t)n, sizeof(int));
+    float* fsum = f ? (float*)calloc((size_t)n * (size_t)fdim, sizeof(float)) : NULL;      /* vector<float>(fdim): zeros */
+    votes_t* votes = c ? (votes_t*)calloc((size_t)n * (size_t)ldim, sizeof(votes_t)) : NULL;
 
     for (int64_t i = 0; i < n; i++) {
         /* :53-56  true fp32 divisions */
@@ -180,6 +232,9 @@ static int64_t subsample_one(const float* p, int64_t n, float dl, float* out)
         sum[3 * node + 0] += p[3 * i + 0];
         sum[3 * node + 1] += p[3 * i + 1];
         sum[3 * node + 2] += p[3 * i + 2];
+        /* grid_subsampling.h:50,67  transform(features, f_begin, plus<float>) */
+        if (f) for (int32_t d = 0; d < fdim; d++) fsum[(size_t)node * fdim + d] += f[(size_t)i * fdim + d];
+        if (c) for (int32_t d = 0; d < ldim; d++) votes_add(&votes[(size_t)node * ldim + d], c[(size_t)i * ldim + d]);
     }
     /* :85-87  iterate the container; point * (float)(1.0 / count) */
     int64_t o = 0;
@@ -188,7 +243,17 @@ static int64_t subsample_one(const float* p, int64_t n, float dl, float* out)
         out[3 * o + 0] = sum[3 * q + 0] * a;
         out[3 * o + 1] = sum[3 * q + 1] * a;
         out[3 * o + 2] = sum[3 * q + 2] * a;
+        if (f) {                                   /* :90-95  f / (float)count */
+            float fc = (float)cnt[q];
+            for (int32_t d = 0; d < fdim; d++) of[(size_t)o * fdim + d] = fsum[(size_t)q * fdim + d] / fc;
+        }
+        if (c) for (int32_t d = 0; d < ldim; d++) oc[(size_t)o * ldim + d] = label_vote_pick(&votes[(size_t)q * ldim + d]);
     }
+    if (votes) {
+        for (int64_t i = 0; i < n * ldim; i++) { free(votes[i].lab); free(votes[i].cnt); }
+        free(votes);
+    }
+    free(fsum);
     free(m.next); free(m.key); free(m.bucket); free(sum); free(cnt);
     return o;
 }
@@ -201,7 +266,7 @@ int64_t oracle_subsample_batch(const float* pts, int64_t n, const int32_t* lens,
     int64_t start = 0, o = 0;
     float* tmp = (float*)malloc(sizeof(float) * 3 * (size_t)(n > 0 ? n : 1));
     for (int32_t b = 0; b < nb; b++) {
-        int64_t m = subsample_one(pts + 3 * start, lens[b], dl, tmp);
+        int64_t m = subsample_one(pts + 3 * start, lens[b], dl, tmp, NULL, 0, NULL, NULL, 0, NULL);
         if (m > maxp) m = maxp;             /* :181-204 keep the head */
         memcpy(out_pts + 3 * o, tmp, sizeof(float) * 3 * (size_t)m);
         out_lens[b] = (int32_t)m;
@@ -210,6 +275,45 @@ int64_t oracle_subsample_batch(const float* pts, int64_t n, const int32_t* lens,
     }
     free(tmp);
     return o;
+}
+
+/* grid_subsampling.cpp:109-211 with features [n, fdim] and / or classes [n, ldim] (NULL = absent).  out_feats holds n*fdim
+ * floats, out_classes n*ldim ints.  Returns total M, or -2 for ldim > 1 with more than one cloud: the reference slices the
+ * classes of the later clouds with a wrong end offset (:157-158) and reads out of bounds, so there is nothing to restate. */
+int64_t oracle_subsample_batch_ex(const float* pts, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p,
+                                  const float* feats, int32_t fdim, const int32_t* classes, int32_t ldim, float* out_pts,
+                                  int32_t* out_lens, float* out_feats, int32_t* out_classes)
+{
+    if (classes && ldim > 1 && nb > 1) return -2;
+    int64_t maxp = max_p < 1 ? n : max_p;
+    int64_t start = 0, o = 0;
+    size_t n1 = (size_t)(n > 0 ? n : 1);
+    float* tmp = (float*)malloc(sizeof(float) * 3 * n1);
+    float* tf = feats ? (float*)malloc(sizeof(float) * n1 * (size_t)fdim) : NULL;
+    int32_t* tc = classes ? (int32_t*)malloc(sizeof(int32_t) * n1 * (size_t)ldim) : NULL;
+    for (int32_t b = 0; b < nb; b++) {
+        int64_t m = subsample_one(pts + 3 * start, lens[b], dl, tmp, feats ? feats + (size_t)start * fdim : NULL, fdim, tf,
+                                  classes ? classes + (size_t)start * ldim : NULL, ldim, tc);
+        if (m > maxp) m = maxp;             /* :181-204 keep the head of points, features and classes alike */
+        memcpy(out_pts + 3 * o, tmp, sizeof(float) * 3 * (size_t)m);
+        if (feats) memcpy(out_feats + (size_t)o * fdim, tf, sizeof(float) * (size_t)m * fdim);
+        if (classes) memcpy(out_classes + (size_t)o * ldim, tc, sizeof(int32_t) * (size_t)m * ldim);
+        out_lens[b] = (int32_t)m;
+        o += m;
+        start += lens[b];
+    }
+    free(tmp); free(tf); free(tc);
+    return o;
+}
+
+/* The vote of one voxel on its own (unit tests of the CUDA vote routine). */
+int32_t oracle_label_vote(const int32_t* labels, int64_t n)
+{
+    votes_t v = { NULL, NULL, 0, 0 };
+    for (int64_t i = 0; i < n; i++) votes_add(&v, labels[i]);
+    int32_t r = label_vote_pick(&v);
+    free(v.lab); free(v.cnt);
+    return r;
 }
 
 /* Voxel key + origin of one cloud, exposed for unit tests of the CUDA key kernel. */

@@ -8,7 +8,9 @@
 // which no longer compiles against numpy 2 (NPY_IN_ARRAY) / py3.12 (numpy.distutils).
 #include "cpp_subsampling/grid_subsampling/grid_subsampling.h"
 #include "cpp_neighbors/neighbors/neighbors.h"
+#include <algorithm>
 #include <cstring>
+#include <unordered_map>
 #include <cstdlib>
 
 extern "C" {
@@ -29,6 +31,39 @@ long ref_subsample_batch(const float* pts, long n, const int* lens, int nb, floa
     std::memcpy(out_pts, subsampled_points.data(), sizeof(float) * 3 * m);
     std::memcpy(out_lens, subsampled_batches.data(), sizeof(int) * nb);
     return m;
+}
+
+// Same with per-point features [n, fdim] and / or integer classes [n, ldim] (nullptr = absent): grid_subsampling.cpp:34-102.
+// out_feats holds cap*fdim floats, out_classes cap*ldim ints.  ldim > 1 with more than one cloud is refused (-2): the reference
+// slices the classes of later clouds with a wrong end offset (grid_subsampling.cpp:157-158), which reads out of bounds.
+long ref_subsample_batch_ex(const float* pts, long n, const int* lens, int nb, float dl, int max_p, const float* feats, int fdim,
+                            const int* classes, int ldim, float* out_pts, long cap, int* out_lens, float* out_feats, int* out_classes)
+{
+    if (classes && ldim > 1 && nb > 1) return -2;
+    std::vector<PointXYZ> original_points((const PointXYZ*)pts, (const PointXYZ*)pts + n);
+    std::vector<int> original_batches(lens, lens + nb);
+    std::vector<PointXYZ> subsampled_points;
+    std::vector<float> of, sf;
+    std::vector<int> oc, sc, subsampled_batches;
+    if (feats) of.assign(feats, feats + (size_t)n * fdim);
+    if (classes) oc.assign(classes, classes + (size_t)n * ldim);
+    batch_grid_subsampling(original_points, subsampled_points, of, sf, oc, sc, original_batches, subsampled_batches, dl, max_p);
+    long m = (long)subsampled_points.size();
+    if (m > cap) return -1;
+    std::memcpy(out_pts, subsampled_points.data(), sizeof(float) * 3 * m);
+    std::memcpy(out_lens, subsampled_batches.data(), sizeof(int) * nb);
+    if (feats) std::memcpy(out_feats, sf.data(), sizeof(float) * sf.size());
+    if (classes) std::memcpy(out_classes, sc.data(), sizeof(int) * sc.size());
+    return m;
+}
+
+// The vote of one voxel exactly as grid_subsampling.h:56-61 + grid_subsampling.cpp:100-101 do it with THIS libstdc++:
+// labels[*it] += 1 in point order, then the first maximal element in the container's iteration order.
+int ref_label_vote(const int* labels, long n)
+{
+    std::unordered_map<int, int> m;
+    for (long i = 0; i < n; i++) m[labels[i]] += 1;
+    return std::max_element(m.begin(), m.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second < b.second; })->first;
 }
 
 // Two-call protocol: the result is kept in a static vector between the calls.

@@ -31,6 +31,10 @@ SIGNATURES = {
     "pcrcg_subsample_ws_bytes": (_SZ, [_I64, _I32]),
     "pcrcg_subsample_batch_dev": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
     "pcrcg_subsample_batch_host": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, C.POINTER(_P), C.POINTER(_I64), _P]),
+    "pcrcg_subsample_ex_ws_bytes": (_SZ, [_I64, _I32, _I32, _I32]),
+    "pcrcg_subsample_batch_ex_dev": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, _P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "pcrcg_subsample_batch_ex_host": (C.c_int, [_P, _I64, _P, _I32, _F, _I32, _P, _I32, _P, _I32, C.POINTER(_P), C.POINTER(_I64), _P,
+                                                C.POINTER(_P), C.POINTER(_P)]),
     "pcrcg_group_starts_dev": (C.c_int, [_P, _I32, _I32, _P, _P, _P]),
     "pcrcg_radius_ws_bytes": (_SZ, [_I64, _I64, _I32]),
     "pcrcg_radius_build_dev": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _SZ, _P]),

@@ -48,6 +48,9 @@ void prof_end(int slot, cudaStream_t st)
 }
 size_t subsample_ws_bytes(int64_t n, int32_t nb);
 int subsample_batch_dev(const float*, int64_t, const int32_t*, int32_t, float, int32_t, float*, int32_t*, void*, size_t, cudaStream_t);
+size_t subsample_ex_ws_bytes(int64_t n, int32_t nb, int32_t fdim, int32_t ldim);
+int subsample_batch_ex_dev(const float*, int64_t, const int32_t*, int32_t, float, int32_t, const float*, int32_t, const int32_t*, int32_t,
+                           float*, int32_t*, float*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int group_starts_dev(const int32_t*, int32_t, int32_t, int32_t*, int32_t*, cudaStream_t);
 size_t radius_ws_bytes(int64_t nq, int64_t ns, int32_t nb);
 int radius_build_dev(const float*, int64_t, const int32_t*, int32_t, float, void*, size_t, cudaStream_t);
@@ -184,6 +187,81 @@ int pcrcg_subsample_batch_host(const float* points, int64_t n, const int32_t* le
     if (e != cudaSuccess) { free(o); set_error("subsample_batch: D2H failed: %s", cudaGetErrorString(e)); return PCRCG_ERR; }
     *out_points = o;
     *out_m = m;
+    return PCRCG_OK;
+}
+
+size_t pcrcg_subsample_ex_ws_bytes(int64_t n, int32_t nb, int32_t fdim, int32_t ldim) { return subsample_ex_ws_bytes(n, nb, fdim, ldim); }
+
+int pcrcg_subsample_batch_ex_dev(const float* points, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p,
+                                 const float* features, int32_t fdim, const int32_t* classes, int32_t ldim, float* out_points,
+                                 int32_t* out_lens, float* out_features, int32_t* out_classes, int32_t* status, void* ws,
+                                 size_t ws_bytes, pcrcg_stream_t stream)
+{
+    return subsample_batch_ex_dev(points, n, lens, nb, dl, max_p, features, fdim, classes, ldim, out_points, out_lens, out_features,
+                                  out_classes, status, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int d2h_new(void** out, const void* dev, size_t bytes)
+{
+    void* o = malloc(bytes > 0 ? bytes : 1);
+    PCRCG_REQUIRE(o != nullptr, "subsample_batch: out of host memory");
+    cudaError_t e = cudaMemcpy(o, dev, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(o); set_error("subsample_batch: D2H failed: %s", cudaGetErrorString(e)); return PCRCG_ERR; }
+    *out = o;
+    return PCRCG_OK;
+}
+
+int pcrcg_subsample_batch_ex_host(const float* points, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p,
+                                  const float* features, int32_t fdim, const int32_t* classes, int32_t ldim, float** out_points,
+                                  int64_t* out_m, int32_t* out_lens, float** out_features, int32_t** out_classes)
+{
+    PCRCG_REQUIRE(points && lens && out_points && out_m && out_lens, "subsample_batch: null argument");
+    PCRCG_REQUIRE((features == nullptr || out_features != nullptr) && (classes == nullptr || out_classes != nullptr), "subsample_batch: null argument");
+    PCRCG_REQUIRE(n >= 1 && nb >= 1, "Error");   // the reference raises RuntimeError("Error") on an empty result
+    if (features == nullptr) fdim = 0;
+    if (classes == nullptr) ldim = 0;
+    DevBuf dp, dl_, dout, dol, dws, df, dc, dof, doc, dst;
+    size_t wsb = subsample_ex_ws_bytes(n, nb, fdim, ldim);
+    PCRCG_TRY(dp.alloc(sizeof(float) * 3 * n));
+    PCRCG_TRY(dl_.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dout.alloc(sizeof(float) * 3 * n));
+    PCRCG_TRY(dol.alloc(sizeof(int32_t) * nb));
+    PCRCG_TRY(dws.alloc(wsb));
+    PCRCG_TRY(dst.alloc(sizeof(int32_t)));
+    PCRCG_CUDA(cudaMemcpy(dp.p, points, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    PCRCG_CUDA(cudaMemcpy(dl_.p, lens, sizeof(int32_t) * nb, cudaMemcpyHostToDevice));
+    if (fdim) {
+        PCRCG_TRY(df.alloc(sizeof(float) * (size_t)n * fdim));
+        PCRCG_TRY(dof.alloc(sizeof(float) * (size_t)n * fdim));
+        PCRCG_CUDA(cudaMemcpy(df.p, features, sizeof(float) * (size_t)n * fdim, cudaMemcpyHostToDevice));
+    }
+    if (ldim) {
+        PCRCG_TRY(dc.alloc(sizeof(int32_t) * (size_t)n * ldim));
+        PCRCG_TRY(doc.alloc(sizeof(int32_t) * (size_t)n * ldim));
+        PCRCG_CUDA(cudaMemcpy(dc.p, classes, sizeof(int32_t) * (size_t)n * ldim, cudaMemcpyHostToDevice));
+    }
+    PCRCG_TRY(subsample_batch_ex_dev(dp.as<float>(), n, dl_.as<int32_t>(), nb, dl, max_p, fdim ? df.as<float>() : nullptr, fdim,
+                                     ldim ? dc.as<int32_t>() : nullptr, ldim, dout.as<float>(), dol.as<int32_t>(), dof.as<float>(),
+                                     doc.as<int32_t>(), dst.as<int32_t>(), dws.p, wsb, 0));
+    PCRCG_CUDA(cudaMemcpy(out_lens, dol.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost));
+    if (ldim) {
+        int32_t status = 0;
+        PCRCG_CUDA(cudaMemcpy(&status, dst.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        PCRCG_REQUIRE(status == 0, "subsample_batch: a voxel holds more than 64 distinct labels in one class column (the tie order of the "
+                      "reference's unordered_map is modelled up to 64)");
+    }
+    int64_t m = 0;
+    for (int b = 0; b < nb; b++) m += out_lens[b];
+    PCRCG_REQUIRE(m >= 1, "Error");
+    void *o = nullptr, *of = nullptr, *oc = nullptr;
+    int rc = d2h_new(&o, dout.p, sizeof(float) * 3 * m);
+    if (rc == PCRCG_OK && fdim) rc = d2h_new(&of, dof.p, sizeof(float) * (size_t)m * fdim);
+    if (rc == PCRCG_OK && ldim) rc = d2h_new(&oc, doc.p, sizeof(int32_t) * (size_t)m * ldim);
+    if (rc != PCRCG_OK) { free(o); free(of); free(oc); return rc; }
+    *out_points = (float*)o;
+    *out_m = m;
+    if (fdim) *out_features = (float*)of;
+    if (ldim) *out_classes = (int32_t*)oc;
     return PCRCG_OK;
 }
 

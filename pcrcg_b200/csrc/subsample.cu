@@ -11,7 +11,12 @@
 //   bbox -> origin/NX/NY -> keys -> hash insert (voxel slot per point) -> stable radix sort by slot
 //   -> run heads (= first occurrence + count) -> scan (first-occurrence rank) -> sequential
 //   barycentres -> per-cloud order emulation -> gather to output.
+// Optional per-point features / integer classes (grid_subsampling.cpp:34-102; not used by the KPConv pyramid,
+// datasets/dataloader.py:289 passes neither): subsample_batch_ex_dev runs the same pipeline and then, from the sorted runs and
+// the final lists it leaves in the workspace, the per-voxel feature means (k_bary_feat), the class votes (k_label_vote,
+// label_vote.h) and their gather into the output order (k_gather_extra).
 #include "common.cuh"
+#include "label_vote.h"
 
 namespace pcrcg {
 
@@ -233,6 +238,78 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const uint64_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// grid_subsampling.h:50,67 (features += f, point order) + .cpp:88-96 (f / (float)count): thread = voxel run head, blockIdx.y
+// strides over the feature columns
+__global__ void __launch_bounds__(256) k_bary_feat(const float* __restrict__ feat, int fdim, const uint32_t* __restrict__ sslot,
+                                                   const uint32_t* __restrict__ sidx, int n, const uint32_t* __restrict__ rank,
+                                                   float* __restrict__ featU)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t s = sslot[j];
+    if (j != 0 && sslot[j - 1] == s) return;
+    size_t u = rank[sidx[j]];
+    for (int d = blockIdx.y; d < fdim; d += gridDim.y) {
+        float sum = 0.f;
+        int cnt = 0;
+        for (int t = j; t < n && sslot[t] == s; t++) {
+            sum = __fadd_rn(sum, feat[(size_t)sidx[t] * fdim + d]);
+            cnt++;
+        }
+        featU[u * fdim + d] = __fdiv_rn(sum, (float)cnt);
+    }
+}
+
+// grid_subsampling.h:56-61 + .cpp:97-102: the vote of every voxel and label column (label_vote.h); *status = 1 when a voxel
+// holds more distinct labels than the order model covers
+__global__ void __launch_bounds__(128) k_label_vote(const int32_t* __restrict__ cls, int ldim, const uint32_t* __restrict__ sslot,
+                                                    const uint32_t* __restrict__ sidx, int n, const uint32_t* __restrict__ rank,
+                                                    int32_t* __restrict__ clsU, int32_t* __restrict__ status)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t s = sslot[j];
+    if (j != 0 && sslot[j - 1] == s) return;
+    size_t u = rank[sidx[j]];
+    for (int d = blockIdx.y; d < ldim; d += gridDim.y) {
+        LabelVote v;
+        v.reset();
+        for (int t = j; t < n && sslot[t] == s; t++) v.add(cls[(size_t)sidx[t] * ldim + d]);
+        if (v.overflow) atomicExch(status, 1);
+        clsU[u * ldim + d] = v.pick();
+    }
+}
+
+// Output row e of cloud c is the voxel L[e] of the cloud's final list (grid_subsampling.cpp:85-102 walks the container once
+// for points, features and classes alike).  k_order starts with L = seqA and swaps the two lists after every epoch.
+__global__ void __launch_bounds__(256) k_gather_extra(const uint32_t* __restrict__ rank, const int32_t* __restrict__ starts,
+                                                      const int32_t* __restrict__ out_lens, const int32_t* __restrict__ out_base,
+                                                      const uint32_t* __restrict__ seqA, const uint32_t* __restrict__ seqB,
+                                                      const float* __restrict__ featU, int fdim, float* __restrict__ out_feat,
+                                                      const int32_t* __restrict__ clsU, int ldim, int32_t* __restrict__ out_cls)
+{
+    const int c = blockIdx.x;
+    const int s0 = starts[c];
+    const uint32_t Ub = rank[s0];
+    const int M = (int)(rank[starts[c + 1]] - Ub);
+    int epochs = 0;
+    for (int done = 0; done < M; epochs++) done = (uint32_t)M < c_sched[epochs] ? M : (int)c_sched[epochs];
+    const uint32_t* L = ((epochs & 1) ? seqB : seqA) + Ub;
+    const int m_out = out_lens[c];
+    const size_t ob = (size_t)out_base[c];
+    if (out_feat != nullptr)
+        for (long long k = threadIdx.x; k < (long long)m_out * fdim; k += blockDim.x) {
+            const long long e = k / fdim, d = k - e * fdim;
+            out_feat[(ob + e) * fdim + d] = featU[((size_t)Ub + L[e]) * fdim + d];
+        }
+    if (out_cls != nullptr)
+        for (long long k = threadIdx.x; k < (long long)m_out * ldim; k += blockDim.x) {
+            const long long e = k / ldim, d = k - e * ldim;
+            out_cls[(ob + e) * ldim + d] = clsU[((size_t)Ub + L[e]) * ldim + d];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct SubWS {
     int32_t* starts; int* bbox; float* origin; uint64_t* nxny; uint64_t* keys; uint32_t* rep; uint32_t* slot;
     uint32_t* iota; uint32_t* sslot; uint32_t* sidx; uint32_t* rank; float* baryU; uint64_t* keyU; int32_t* out_base;
@@ -309,6 +386,66 @@ int subsample_batch_dev(const float* pts, int64_t n, const int32_t* lens, int32_
     PCRCG_TRY(cloud_starts(out_lens, nb, s.out_base, st));
     k_order<<<nb, ORD_THREADS, 0, st>>>(s.keyU, s.rank, s.starts, out_lens, s.out_base, s.baryU, out_pts,
                                         s.seqA, s.seqB, s.nxt, s.aux, s.rr, s.ff, s.head);
+    PCRCG_CUDA(cudaGetLastError());
+    return PCRCG_OK;
+}
+
+// Workspace of the variant with features / classes: the plain layout first (so that subsample_batch_dev finds its buffers where
+// it always does), then the per-voxel feature means and votes in first-occurrence order.
+static size_t sub_layout_ex(Workspace& W, int64_t n, int32_t nb, int32_t fdim, int32_t ldim, SubWS* o, float** featU, int32_t** clsU)
+{
+    sub_layout(W, n, nb, o);
+    size_t n1 = (size_t)(n > 0 ? n : 1);
+    float* f = W.take<float>(n1 * (size_t)(fdim > 0 ? fdim : 0) + 1);
+    int32_t* c = W.take<int32_t>(n1 * (size_t)(ldim > 0 ? ldim : 0) + 1);
+    if (featU) *featU = f;
+    if (clsU) *clsU = c;
+    return W.off;
+}
+
+size_t subsample_ex_ws_bytes(int64_t n, int32_t nb, int32_t fdim, int32_t ldim)
+{
+    Workspace W(nullptr, 0);
+    return sub_layout_ex(W, n, nb, fdim, ldim, nullptr, nullptr, nullptr) + 256;
+}
+
+// features [n, fdim] / classes [n, ldim] may each be nullptr (then its dim is ignored).  out_features [n, fdim], out_classes
+// [n, ldim] (upper bounds, like out_pts).  status (device int32, required with classes): set to 1 when some voxel holds more than
+// LV_CAP distinct labels in one column (its vote is then not the reference's); the caller reads it when it next synchronises.
+int subsample_batch_ex_dev(const float* pts, int64_t n, const int32_t* lens, int32_t nb, float dl, int32_t max_p, const float* features,
+                           int32_t fdim, const int32_t* classes, int32_t ldim, float* out_pts, int32_t* out_lens, float* out_features,
+                           int32_t* out_classes, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    PCRCG_REQUIRE(features == nullptr || (fdim >= 1 && fdim <= 65535 && out_features != nullptr), "subsample: features need 1 <= fdim <= 65535 and an output");
+    PCRCG_REQUIRE(classes == nullptr || (ldim >= 1 && ldim <= 65535 && out_classes != nullptr && status != nullptr),
+                  "subsample: classes need 1 <= ldim <= 65535, an output and a status word");
+    // grid_subsampling.cpp:157-158 slices the classes of every cloud after the first with a wrong end offset when ldim > 1
+    // (reads out of bounds): there is no reference behaviour to reproduce
+    PCRCG_REQUIRE(classes == nullptr || ldim == 1 || nb == 1, "subsample: classes with more than one column are defined for a single cloud only "
+                  "(the reference mis-slices them for later clouds, grid_subsampling.cpp:157-158)");
+    if (features == nullptr) fdim = 0;
+    if (classes == nullptr) ldim = 0;
+    Workspace W(ws, ws_bytes);
+    SubWS s;
+    float* featU = nullptr;
+    int32_t* clsU = nullptr;
+    sub_layout_ex(W, n, nb, fdim, ldim, &s, &featU, &clsU);
+    PCRCG_REQUIRE(ws != nullptr && W.ok(), "subsample: workspace too small (%zu < %zu)", ws_bytes, W.off);
+    PCRCG_TRY(subsample_batch_dev(pts, n, lens, nb, dl, max_p, out_pts, out_lens, ws, ws_bytes, st));
+    if (fdim == 0 && ldim == 0) return PCRCG_OK;
+    const int N = (int)n;
+    count_launches((fdim ? 1 : 0) + (ldim ? 1 : 0) + 1);
+    if (fdim) {
+        const dim3 g((unsigned)cdiv64(N > 0 ? N : 1, 256), (unsigned)(fdim < 64 ? fdim : 64));
+        k_bary_feat<<<g, 256, 0, st>>>(features, fdim, s.sslot, s.sidx, N, s.rank, featU);
+    }
+    if (ldim) {
+        PCRCG_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+        const dim3 g((unsigned)cdiv64(N > 0 ? N : 1, 128), (unsigned)(ldim < 64 ? ldim : 64));
+        k_label_vote<<<g, 128, 0, st>>>(classes, ldim, s.sslot, s.sidx, N, s.rank, clsU, status);
+    }
+    k_gather_extra<<<nb, 256, 0, st>>>(s.rank, s.starts, out_lens, s.out_base, s.seqA, s.seqB, featU, fdim, fdim ? out_features : nullptr,
+                                       clsU, ldim, ldim ? out_classes : nullptr);
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }

@@ -30,10 +30,11 @@ def _dev_i32(t, device):
 
 def batch_grid_subsampling_kpconv(points, batches_len, features=None, labels=None, sampleDl=0.1, max_p=0, verbose=0,
                                   random_grid_orient=True):
-    """-> (s_points [M,3] f32, s_len [B] i32), on the device of ``points`` (cuda)."""
-    if features is not None or labels is not None:
-        raise NotImplementedError("pcrcg_b200: features/labels subsampling is outside the KPConv hot path")
-    return ops.subsample_batch(points, batches_len, sampleDl, max_p)
+    """-> (s_points [M,3] f32, s_len [B] i32[, s_features][, s_labels]) in the reference's order (datasets/dataloader.py:18-52),
+    on the device of ``points`` (cuda)."""
+    if features is None and labels is None:
+        return ops.subsample_batch(points, batches_len, sampleDl, max_p)
+    return ops.subsample_batch_ex(points, batches_len, sampleDl, max_p, features=features, classes=labels)
 
 
 def batch_neighbors_kpconv(queries, supports, q_batches, s_batches, radius, max_neighbors):

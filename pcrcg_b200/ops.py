@@ -77,6 +77,57 @@ def subsample_batch(points, lens, sampleDl, max_p=0):
     return out[:m], out_lens
 
 
+def subsample_batch_ex(points, lens, sampleDl, max_p=0, features=None, classes=None):
+    """Grid subsampling with per-point features [N, d] f32 and / or classes [N] or [N, d] i32 (grid_subsampling.cpp:34-102), all
+    cuda -> (s_points, s_lens[, s_features [M, d]][, s_classes [M, d]]) in the reference's tuple order (wrapper.cpp:318-326).
+    One host sync (M and the status word of the class votes)."""
+    if features is None and classes is None:
+        return subsample_batch(points, lens, sampleDl, max_p)
+    _need_cuda(points, lens)
+    points, lens = _f32c(points), _i32c(lens)
+    n, nb = points.shape[0], lens.shape[0]
+    f = c = None
+    fdim, ldim = 0, 1
+    if features is not None:
+        _need_cuda(features)
+        f = _f32c(features)
+        if f.dim() != 2 or f.shape[0] != n or f.shape[1] < 1:
+            raise RuntimeError("Wrong dimensions : features.shape is not (N, d)")
+        fdim = f.shape[1]
+    if classes is not None:
+        _need_cuda(classes)
+        c = _i32c(classes)
+        if c.dim() not in (1, 2) or c.shape[0] != n or (c.dim() == 2 and c.shape[1] < 1):
+            raise RuntimeError("Wrong dimensions : classes.shape is not (N,) or (N, d)")
+        ldim = c.shape[1] if c.dim() == 2 else 1
+    L = lib()
+    dev = points.device
+    with torch.cuda.device(dev):
+        ws = _ws(L.pcrcg_subsample_ex_ws_bytes(n, nb, fdim, ldim if c is not None else 0), dev)
+        out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+        out_lens = torch.empty(nb, dtype=torch.int32, device=dev)
+        of = torch.empty((max(n, 1), fdim), dtype=torch.float32, device=dev) if f is not None else None
+        oc = torch.empty((max(n, 1), ldim), dtype=torch.int32, device=dev) if c is not None else None
+        tot = torch.zeros(2, dtype=torch.int32, device=dev)           # [M, status]
+        check(L.pcrcg_subsample_batch_ex_dev(points.data_ptr(), n, lens.data_ptr(), nb, float(sampleDl), int(max_p),
+                                             f.data_ptr() if f is not None else None, fdim, c.data_ptr() if c is not None else None, ldim,
+                                             out.data_ptr(), out_lens.data_ptr(), of.data_ptr() if of is not None else None,
+                                             oc.data_ptr() if oc is not None else None, tot[1:].data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _stream()))
+        gs = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+        check(L.pcrcg_group_starts_dev(out_lens.data_ptr(), nb, 1, gs.data_ptr(), tot.data_ptr(), _stream()))
+        m, status = tot.tolist()
+    if status != 0:
+        raise RuntimeError("subsample_batch: a voxel holds more than 64 distinct labels in one class column (the tie order of the "
+                           "reference's unordered_map is modelled up to 64)")
+    res = [out[:m], out_lens]
+    if of is not None:
+        res.append(of[:m])
+    if oc is not None:
+        res.append(oc[:m])
+    return tuple(res)
+
+
 class RadiusGrid:
     """Support cloud binned for radius search (pcrcg_radius_build_dev); query it any number of times."""
 

@@ -63,19 +63,23 @@ def test_ops_refuse_cpu_tensors():
                            torch.zeros(15, 3), torch.zeros(15, 1, 8), 0.05)
 
 
-def test_features_and_classes_are_refused_loudly():
-    """the feature / label outputs of the reference's subsample_batch are outside the hot path; the
-    drop-in refuses them instead of silently returning two arrays less (no GPU needed: the check precedes every device call)"""
+def test_features_and_classes_argument_checks():
+    """subsample_batch(features=, classes=): the reference's argument errors (wrapper.cpp:176-246) are raised before any device
+    call, and the one case the reference leaves undefined is refused (no GPU needed)"""
     import numpy as np
     from pcrcg_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as cpp_subsampling
-    from pcrcg_b200 import dataloader
     pts = np.zeros((4, 3), np.float32)
-    for kw in (dict(features=np.ones((4, 2), np.float32)), dict(classes=np.zeros((4, 1), np.int32))):
-        with pytest.raises(NotImplementedError, match="outside the KPConv hot path"):
-            cpp_subsampling.subsample_batch(pts, [4], sampleDl=0.1, **kw)
-        with pytest.raises(NotImplementedError, match="outside the KPConv hot path"):
-            cpp_subsampling.subsample(pts, sampleDl=0.1, **kw)
-    with pytest.raises(NotImplementedError):
-        dataloader.batch_grid_subsampling_kpconv(pts, [4], features=np.ones((4, 2), np.float32))
+    with pytest.raises(RuntimeError, match=r"features.shape is not \(N, d\)"):
+        cpp_subsampling.subsample_batch(pts, [4], features=np.ones(4, np.float32))
+    with pytest.raises(RuntimeError, match=r"features.shape is not \(N, d\)"):
+        cpp_subsampling.subsample_batch(pts, [4], features=np.ones((3, 2), np.float32))
+    with pytest.raises(RuntimeError, match=r"classes.shape is not \(N,\) or \(N, d\)"):
+        cpp_subsampling.subsample_batch(pts, [4], classes=np.zeros((4, 1, 1), np.int32))
+    with pytest.raises(RuntimeError, match=r"classes.shape is not \(N,\) or \(N, d\)"):
+        cpp_subsampling.subsample_batch(pts, [4], classes=np.zeros(5, np.int32))
+    with pytest.raises(RuntimeError, match="single cloud only"):
+        cpp_subsampling.subsample_batch(pts, [2, 2], classes=np.zeros((4, 2), np.int32))
+    with pytest.raises(RuntimeError, match="Error converting input features"):
+        cpp_subsampling.subsample_batch(pts, [4], features=[["a", "b"]] * 4)
     with pytest.raises(RuntimeError, match="Error parsing method"):
         cpp_subsampling.subsample_batch(pts, [4], method="nonsense")

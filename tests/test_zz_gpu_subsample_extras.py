@@ -1,0 +1,95 @@
+"""GPU parity: subsample_batch(features=, classes=) -- grid_subsampling.cpp:34-102, wrapper.cpp:103-326 -- through the host C-ABI
+entry (the reference's module mirror) and the device entry, bit for bit against the CPU oracle (oracle/port.c, pinned to the
+unmodified reference core by tests/test_label_vote_host.py).
+
+Written after this round's GPU budget was spent: the CUDA kernels behind it (k_bary_feat, k_label_vote, k_gather_extra) have
+not run on a B200 yet; the per-voxel vote routine itself is pinned on the CPU.  The file sorts last on purpose."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from pcrcg_b200 import dataloader, ops
+from pcrcg_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as cpp_subsampling
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _case(seed, nb, n_per, extent, fdim, ldim, n_labels):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(max(1, n_per // 2), n_per + 1, size=nb).astype(np.int32)
+    n = int(lens.sum())
+    pts = (rng.random((n, 3)) * extent).astype(np.float32)
+    f = rng.standard_normal((n, fdim)).astype(np.float32)
+    c = rng.integers(-2, n_labels - 2, size=(n, ldim)).astype(np.int32)
+    return pts, lens, f, c
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        y = y.cpu().numpy() if torch.is_tensor(y) else y
+        assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("seed,nb,n_per,extent,dl,n_labels", [
+    (0, 3, 4000, 1.0, 0.1, 4),          # a few points and labels per voxel: frequent two-way ties
+    (1, 2, 3000, 0.3, 0.1, 40),         # crowded voxels: up to ~40 distinct labels, the 13 -> 29 -> 59 bucket rehashes
+    (2, 1, 500, 1.0, 0.05, 3),          # one cloud, mostly single-point voxels
+    (3, 4, 2000, 2.0, 0.25, 12),
+])
+def test_features_and_classes_match_the_reference(port, seed, nb, n_per, extent, dl, n_labels):
+    pts, lens, f, c = _case(seed, nb, n_per, extent, 5, 1, n_labels)
+    for kw in (dict(features=f), dict(classes=c), dict(features=f, classes=c), dict(classes=c[:, 0])):
+        want = port.subsample_batch_ex(pts, lens, sampleDl=dl, **kw)
+        _same(want, cpp_subsampling.subsample_batch(pts, lens, sampleDl=dl, **kw))                      # host buffers, C ABI
+        dkw = {k: _t(v) for k, v in kw.items()}
+        _same(want, ops.subsample_batch_ex(_t(pts), _t(lens), dl, **dkw))                               # device entry
+    want = port.subsample_batch_ex(pts, lens, features=f, classes=c, sampleDl=dl)
+    _same(want, dataloader.batch_grid_subsampling_kpconv(_t(pts), _t(lens), features=_t(f), labels=_t(c), sampleDl=dl))
+
+
+def test_points_and_lens_unchanged_by_the_extras(port):
+    pts, lens, f, c = _case(7, 3, 3000, 1.0, 3, 1, 5)
+    gp, gl = cpp_subsampling.subsample_batch(pts, lens, sampleDl=0.1)
+    ep, el, _, _ = cpp_subsampling.subsample_batch(pts, lens, features=f, classes=c, sampleDl=0.1)
+    assert np.array_equal(gp, ep) and np.array_equal(gl, el)
+
+
+def test_max_p_truncates_features_and_classes_alike(port):
+    pts, lens, f, c = _case(4, 3, 3000, 1.0, 2, 1, 6)
+    want = port.subsample_batch_ex(pts, lens, features=f, classes=c, sampleDl=0.1, max_p=57)
+    assert want[1].tolist() == [57, 57, 57]
+    _same(want, cpp_subsampling.subsample_batch(pts, lens, features=f, classes=c, sampleDl=0.1, max_p=57))
+
+
+def test_multi_column_classes_single_cloud(port):
+    pts, lens, f, c = _case(5, 1, 5000, 1.0, 1, 3, 7)
+    want = port.subsample_batch_ex(pts, lens, classes=c, sampleDl=0.1)
+    _same(want, cpp_subsampling.subsample_batch(pts, lens, classes=c, sampleDl=0.1))
+    sp, sc = cpp_subsampling.subsample(pts, classes=c, sampleDl=0.1)                                   # wrapper.cpp:546-553
+    assert np.array_equal(sp, want[0]) and np.array_equal(sc, want[2])
+
+
+def test_all_points_in_one_voxel_many_tied_labels(port):
+    """every label occurs once: the answer is purely the container's iteration order, through three rehashes"""
+    rng = np.random.default_rng(6)
+    for D in (1, 2, 13, 14, 29, 30, 59, 60, 64):
+        pts = (rng.random((D, 3)) * 0.01).astype(np.float32)
+        c = (rng.permutation(1000)[:D] - 500).astype(np.int32)
+        want = port.subsample_batch_ex(pts, [D], classes=c, sampleDl=1.0)
+        assert len(want[0]) == 1
+        _same(want, cpp_subsampling.subsample_batch(pts, [D], classes=c, sampleDl=1.0))
+
+
+def test_more_than_64_distinct_labels_in_a_voxel_is_reported():
+    pts = np.zeros((65, 3), np.float32)
+    with pytest.raises(RuntimeError, match="more than 64 distinct labels"):
+        cpp_subsampling.subsample_batch(pts, [65], classes=np.arange(65, dtype=np.int32), sampleDl=1.0)
+    with pytest.raises(RuntimeError, match="more than 64 distinct labels"):
+        ops.subsample_batch_ex(_t(pts), _t(np.array([65], np.int32)), 1.0, classes=_t(np.arange(65, dtype=np.int32)))
