@@ -16,6 +16,8 @@ Multi GPU: launched by torchrun, one rank per GPU, pairs sharded by rank, no col
 import argparse
 import json
 import os
+import select
+import signal
 import statistics
 import subprocess
 import sys
@@ -170,6 +172,71 @@ def cpu_reference_run(pairs, cfg, limits, state_dict, threads, views_np=None):
             bp.encoder(x, batch, blocks_desc)
     t_enc = time.perf_counter() - t0
     return len(pairs) / (t_pre + t_enc), kind, dict(preprocess_s=round(t_pre, 3), encoder_s=round(t_enc, 3), workers=workers)
+
+
+# ------------------------------------------------------------------------------------------------
+class HeadlineGuard:
+    """The headline measurement must reach stdout whatever happens afterwards.  Once the two timed regions of the main workload
+    are over, rank 0 arms this guard with the finished JSON line; the brief measurements of the other workloads and the CPU
+    parity check that follow run under it.  If they do not finish within ``deadline_s``, or the process is told to terminate
+    (SIGTERM from the launcher because another rank died, or from whoever enforces a time limit), a watcher thread prints the
+    line -- marked as such -- and ends the process.  The thread is woken through signal.set_wakeup_fd, which the C-level signal
+    handler writes to even while the main thread is blocked inside a CUDA or NCCL call."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.done = False
+        self.line = None
+
+    def arm(self, line, deadline_s, out=None):
+        self.line = dict(line)
+        out = out if out is not None else sys.stdout
+        r, w = os.pipe()
+        os.set_blocking(w, False)
+        try:
+            signal.signal(signal.SIGTERM, lambda *a: None)
+            signal.set_wakeup_fd(w, warn_on_full_buffer=False)
+        except ValueError:                     # not the main thread: deadline only
+            pass
+
+        def watch():
+            t_end = time.monotonic() + deadline_s
+            why = None
+            while why is None:
+                left = t_end - time.monotonic()
+                if left <= 0:
+                    why = f"did not finish within {deadline_s:.0f} s after the main measurement"
+                    break
+                ready, _, _ = select.select([r], [], [], left)
+                if ready:
+                    sig = os.read(r, 1)
+                    if sig and sig[0] in (signal.SIGTERM, signal.SIGINT):
+                        why = f"process received signal {sig[0]} after the main measurement"
+            timed_out = why.startswith("did not")
+            with self.lock:
+                printed_here = not self.done
+                if printed_here:
+                    self.done = True
+                    line = dict(self.line)
+                    line["incomplete"] = "other_workloads / parity_check: " + why
+                    out.write(json.dumps(line) + "\n")
+                    out.flush()
+            if not timed_out:
+                os._exit(143)                  # terminated: the line (complete or headline only) is out
+            if printed_here:
+                os._exit(0)                    # the tail is stuck: the headline is out, nothing else is worth waiting for
+        threading.Thread(target=watch, daemon=True).start()
+
+    def finish(self, line, out=None):
+        """prints the complete line unless the watcher already printed the headline; returns whether it did"""
+        out = out if out is not None else sys.stdout
+        with self.lock:
+            if self.done:
+                return False
+            self.done = True
+            out.write(json.dumps(line) + "\n")
+            out.flush()
+        return True
 
 
 # ------------------------------------------------------------------------------------------------
@@ -377,6 +444,28 @@ def quick_measure(workload, P, K, W, rank, world, dev, flush, dist):
     return {"workload": workload, "pairs_per_step_per_gpu": P, "steps": K, "warmup": W, "value": world * P * K / (ms / 1000.0), "unit": UNIT,
             "ms_per_step": ms / K, "e2e_value": world * P * K / (e2e_ms / 1000.0), "points_per_level": [int(p.shape[0]) for p in batch["points"]],
             "limits": list(limits), "list_widths": [int(t.shape[1]) for t in batch["neighbors"]]}
+
+
+def _parity_of_batch(args, pairs, batch, y, path, cfg, limits, views_np, views_dev, pts_dev, lens_dev, P):
+    """pair `--parity-pair` of the stacked batch that was timed vs the reference run on that pair alone on the CPU"""
+    import torch
+    from oracle import checks
+    kq = min(args.parity_pair, P - 1)
+    cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
+    n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
+    seg = batch["pair_segments"][-1].cpu().tolist()
+    x_cpu, x_equal = None, None
+    if views_np is not None:                          # colour: the un-projected input rows of the pair, bit for bit
+        from pcrcg_b200 import projection
+        x_cpu = cpu_unproject(pairs[kq], views_np[2 * kq:2 * kq + 2])
+        x_dev = projection.unproject_features_batch(pts_dev, lens_dev, views_dev)
+        st0 = int(batch["pair_segments"][0][kq].item())
+        x_equal = bool(np.array_equal(x_dev[st0:st0 + x_cpu.shape[0]].cpu().numpy(), x_cpu))
+    enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg, x=x_cpu)
+    return {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
+            "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "unprojected_rows_equal": x_equal,
+            "ok": (not bad) and enc_err < 1e-3 and x_equal is not False,
+            "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
 
 
 def main():
@@ -616,34 +705,7 @@ def main():
     value = world * P * K / (ms_total / 1000.0)
     e2e_value = world * P * K / (e2e_ms / 1000.0)
 
-    extras = []
-    if args.workload == "3dmatch" and args.extra_workloads:
-        for item in args.extra_workloads.split(","):
-            wl, _, pp_ = item.partition(":")
-            extras.append(quick_measure(wl, int(pp_ or 16), max(3, min(K, 5)), 3, rank, world, dev, flush, dist if world > 1 else None))
-
-    # ---- parity of THIS batch, AFTER every timed region (its CPU work must not disturb them): one pair of the stacked run vs the reference run on that pair
-    # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
-    parity = None
-    if rank == 0 and not args.no_parity_check:
-        from oracle import checks
-        kq = min(args.parity_pair, P - 1)
-        cpu_pyr = checks.cpu_pyramid(pairs[kq][0], pairs[kq][1], limits, cfg.first_subsampling_dl, cfg.conv_radius, cfg.num_layers)
-        n_arr, bad = checks.compare_pair(batch, kq, cpu_pyr)
-        seg = batch["pair_segments"][-1].cpu().tolist()
-        x_cpu, x_equal = None, None
-        if views_np is not None:                          # colour: the un-projected input rows of the pair, bit for bit
-            from pcrcg_b200 import projection
-            x_cpu = cpu_unproject(pairs[kq], views_np[2 * kq:2 * kq + 2])
-            x_dev = projection.unproject_features_batch(pts_dev, lens_dev, views_dev)
-            st0 = int(batch["pair_segments"][0][kq].item())
-            x_equal = bool(np.array_equal(x_dev[st0:st0 + x_cpu.shape[0]].cpu().numpy(), x_cpu))
-        enc_err = checks.encoder_error(y[seg[kq]:seg[kq + 1]], cpu_pyr, path.encoder.state_dict(), cfg, x=x_cpu)
-        parity = {"pair": kq, "arrays_compared": n_arr, "index_lists_equal": not bad, "mismatches": bad,
-                  "encoder_max_rel_err": enc_err, "encoder_tolerance": 1e-3, "unprojected_rows_equal": x_equal,
-                  "ok": (not bad) and enc_err < 1e-3 and x_equal is not False,
-                  "oracle": cpu_pyr["kind"] + " C++ subsample/search (canonical (d2, index) ties) + oracle/blocks_port.py encoder"}
-
+    line, guard = None, None
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -705,11 +767,44 @@ def main():
                 "gpu_launches": launches, "roofline": roof, "kernels": kernels}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        # from here on the headline is safe: it is printed even if what follows hangs, dies or is cut off by a time limit
+        guard = HeadlineGuard()
+        guard.arm(line, float(os.environ.get("PCRCG_BENCH_TAIL_DEADLINE_S", "420")))
+
+    # ---- the other workloads of BASELINE.json, briefly, in the same run.  A failure here must not cost the headline: it is
+    # recorded in the line instead (a CUDA error is sticky, so nothing else is attempted on the device after one) ----------------
+    extras = []
+    device_ok = True
+    if args.workload == "3dmatch" and args.extra_workloads:
+        for item in args.extra_workloads.split(","):
+            wl, _, pp_ = item.partition(":")
+            try:
+                extras.append(quick_measure(wl, int(pp_ or 16), max(3, min(K, 5)), 3, rank, world, dev, flush, dist if world > 1 else None))
+            except Exception as e:                    # noqa: BLE001
+                extras.append({"workload": wl, "error": f"{type(e).__name__}: {e}"[:400]})
+                device_ok = False
+                break
+
+    # ---- parity of THIS batch, AFTER every timed region (its CPU work must not disturb them): one pair of the stacked run vs the reference run on that pair
+    # alone on the CPU (oracle/checks.py: all 13 index lists array_equal, encoder output normwise) -----------------------
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        try:
+            parity = _parity_of_batch(args, pairs, batch, y, path, cfg, limits, views_np, views_dev, pts_dev, lens_dev, P)
+        except Exception as e:                        # noqa: BLE001
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"[:400]}
+
+    if rank == 0:
         if parity is not None:
             line["parity_check"] = parity
         if extras:
             line["other_workloads"] = extras
-        print(json.dumps(line), flush=True)
+        guard.finish(line)
+    if not device_ok:
+        # the CUDA context is unusable: no orderly NCCL teardown.  Several ranks: a non-zero exit makes the launcher stop the
+        # others at once (rank 0 then prints its headline from the guard); one rank: the line is out and says what failed
+        sys.stdout.flush()
+        os._exit(1 if world > 1 else 0)
     if world > 1:
         dist.destroy_process_group()
 
