@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_kpconv_fused(
             const int i = m >> 3, row = m & 7, slot = i % FZ_SLOTS;
             if (i >= FZ_SLOTS && lds_acquire(tiles_issued) < i - (FZ_SLOTS - 1)) {   // the slot's previous tile (i - 3) has been issued
                 const long long t0 = clock64();
+                uint32_t probes = 0;
                 while (lds_acquire(tiles_issued) < i - (FZ_SLOTS - 1)) {
                     __nanosleep(32);
-                    if (clock64() - t0 > kSpinLimitCycles) __trap();
+                    if (spin_expired(probes, t0)) __trap();
                 }
             }
             mbar_wait(empty_bar(slot), (uint32_t)(((i / FZ_SLOTS) & 1) ^ 1));       // ... and its MMAs are done

@@ -33,14 +33,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Watchdog of every spin in the tcgen05 kernels: a wait that lasts longer than ~10 s of SM cycles (legitimate waits are
 // microseconds) is a protocol bug; the kernel then TRAPS -- the launch fails with a CUDA error that the host reports --
-// instead of hanging the GPU.  The clock is read only on the slow path (first probe failed).
+// instead of hanging the GPU.  Both conditions must hold, more than 2^20 failed probes AND ~10 s on the SM clock, so that a
+// kernel that was merely switched out for a long time (the clock runs on, the loop does not) is not mistaken for a stuck one;
+// the clock is read only on that slow path.
 constexpr long long kSpinLimitCycles = 20000000000LL;
+constexpr uint32_t kSpinMinProbes = 1u << 20;
+__device__ __forceinline__ bool spin_expired(uint32_t& probes, long long t0)
+{
+    if (probes < kSpinMinProbes) { probes++; return false; }
+    return clock64() - t0 > kSpinLimitCycles;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t probes = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kSpinLimitCycles) __trap();
+        if (spin_expired(probes, t0)) __trap();
     }
 }
 __device__ __forceinline__ int lds_acquire(uint32_t addr)
