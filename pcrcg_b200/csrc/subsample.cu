@@ -16,7 +16,7 @@
 // the final lists it leaves in the workspace, the per-voxel feature means (k_bary_feat), the class votes (k_label_vote,
 // label_vote.h) and their gather into the output order (k_gather_extra).
 #include "common.cuh"
-#include "label_vote.h"
+#include "subsample_extras.h"
 
 namespace pcrcg {
 
@@ -238,75 +238,31 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order(const uint64_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid_subsampling.h:50,67 (features += f, point order) + .cpp:88-96 (f / (float)count): thread = voxel run head, blockIdx.y
-// strides over the feature columns
+// Feature means, class votes and their gather into the output order (thread bodies: subsample_extras.h)
 __global__ void __launch_bounds__(256) k_bary_feat(const float* __restrict__ feat, int fdim, const uint32_t* __restrict__ sslot,
                                                    const uint32_t* __restrict__ sidx, int n, const uint32_t* __restrict__ rank,
                                                    float* __restrict__ featU)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t s = sslot[j];
-    if (j != 0 && sslot[j - 1] == s) return;
-    size_t u = rank[sidx[j]];
-    for (int d = blockIdx.y; d < fdim; d += gridDim.y) {
-        float sum = 0.f;
-        int cnt = 0;
-        for (int t = j; t < n && sslot[t] == s; t++) {
-            sum = __fadd_rn(sum, feat[(size_t)sidx[t] * fdim + d]);
-            cnt++;
-        }
-        featU[u * fdim + d] = __fdiv_rn(sum, (float)cnt);
-    }
+    bary_feat_thread((int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y, (int)gridDim.y, feat, fdim, sslot, sidx, n, rank, featU);
 }
 
-// grid_subsampling.h:56-61 + .cpp:97-102: the vote of every voxel and label column (label_vote.h); *status = 1 when a voxel
-// holds more distinct labels than the order model covers
+// *status = 1 when a voxel holds more distinct labels than the order model covers
 __global__ void __launch_bounds__(128) k_label_vote(const int32_t* __restrict__ cls, int ldim, const uint32_t* __restrict__ sslot,
                                                     const uint32_t* __restrict__ sidx, int n, const uint32_t* __restrict__ rank,
                                                     int32_t* __restrict__ clsU, int32_t* __restrict__ status)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t s = sslot[j];
-    if (j != 0 && sslot[j - 1] == s) return;
-    size_t u = rank[sidx[j]];
-    for (int d = blockIdx.y; d < ldim; d += gridDim.y) {
-        LabelVote v;
-        v.reset();
-        for (int t = j; t < n && sslot[t] == s; t++) v.add(cls[(size_t)sidx[t] * ldim + d]);
-        if (v.overflow) atomicExch(status, 1);
-        clsU[u * ldim + d] = v.pick();
-    }
+    if (label_vote_thread((int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y, (int)gridDim.y, cls, ldim, sslot, sidx, n, rank, clsU))
+        atomicExch(status, 1);
 }
 
-// Output row e of cloud c is the voxel L[e] of the cloud's final list (grid_subsampling.cpp:85-102 walks the container once
-// for points, features and classes alike).  k_order starts with L = seqA and swaps the two lists after every epoch.
 __global__ void __launch_bounds__(256) k_gather_extra(const uint32_t* __restrict__ rank, const int32_t* __restrict__ starts,
                                                       const int32_t* __restrict__ out_lens, const int32_t* __restrict__ out_base,
                                                       const uint32_t* __restrict__ seqA, const uint32_t* __restrict__ seqB,
                                                       const float* __restrict__ featU, int fdim, float* __restrict__ out_feat,
                                                       const int32_t* __restrict__ clsU, int ldim, int32_t* __restrict__ out_cls)
 {
-    const int c = blockIdx.x;
-    const int s0 = starts[c];
-    const uint32_t Ub = rank[s0];
-    const int M = (int)(rank[starts[c + 1]] - Ub);
-    int epochs = 0;
-    for (int done = 0; done < M; epochs++) done = (uint32_t)M < c_sched[epochs] ? M : (int)c_sched[epochs];
-    const uint32_t* L = ((epochs & 1) ? seqB : seqA) + Ub;
-    const int m_out = out_lens[c];
-    const size_t ob = (size_t)out_base[c];
-    if (out_feat != nullptr)
-        for (long long k = threadIdx.x; k < (long long)m_out * fdim; k += blockDim.x) {
-            const long long e = k / fdim, d = k - e * fdim;
-            out_feat[(ob + e) * fdim + d] = featU[((size_t)Ub + L[e]) * fdim + d];
-        }
-    if (out_cls != nullptr)
-        for (long long k = threadIdx.x; k < (long long)m_out * ldim; k += blockDim.x) {
-            const long long e = k / ldim, d = k - e * ldim;
-            out_cls[(ob + e) * ldim + d] = clsU[((size_t)Ub + L[e]) * ldim + d];
-        }
+    gather_extra_thread((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, rank, starts, out_lens, out_base, seqA, seqB, c_sched, featU,
+                        fdim, out_feat, clsU, ldim, out_cls);
 }
 
 // ------------------------------------------------------------------------------------------------
