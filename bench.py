@@ -348,6 +348,7 @@ def algorithmic_work(batch, cfg, limits, enc, views=None):
             rad += 12 * N[l] + 12 * N[l + 1] + 8 * B + 4 * N[l] * W["upsamples"][l]
     work["radius"] = dict(bytes=rad, flops=0)
     agg_b = agg_f = gemm_f = gemm_b = lin_f = lin_b = 0
+    gather_two = gather_fused = 0           # neighbour-feature bytes gathered from L2 (4 bytes per listed element and channel)
     K = cfg.num_kernel_points
     for m in enc.encoder_blocks:
         l = m.layer_ind
@@ -360,6 +361,10 @@ def algorithmic_work(batch, cfg, limits, enc, views=None):
         agg_f += 2 * nq * K * H * cin + 12 * nq * H * K
         gemm_f += 2 * nq * K * cin * cout
         gemm_b += 4 * K * cin * cout + 4 * nq * cout
+        if cin == 64 and cout == 64:        # the layers the one-kernel KPConv takes by default
+            gather_fused += 4 * nq * H * cin
+        else:
+            gather_two += 4 * nq * H * cin
         if isinstance(m, blocks.ResnetBottleneckBlock):
             for u, rows in ((m.unary1, ns), (m.unary2, nq), (m.unary_shortcut, nq)):
                 if isinstance(u, blocks.UnaryBlock):
@@ -369,13 +374,76 @@ def algorithmic_work(batch, cfg, limits, enc, views=None):
         nv = sum(len(v) for v in views)
         C2, Hh, Ww = views[0][0]["feature2d"].shape
         work["projection"] = dict(bytes=12 * N[0] + 4 * Hh * Ww * nv + 4 * N[0] * C2 + 4 * N[0] * (C2 + 1), flops=0)
-    work["kpconv_aggregate"] = dict(bytes=agg_b, flops=agg_f)
+    work["kpconv_aggregate"] = dict(bytes=agg_b, flops=agg_f, gathered_bytes=gather_two)
+    work["kpconv_fused"] = dict(bytes=0, flops=0, gathered_bytes=gather_fused)
     # the KPConv [K*Cin] x Cout contraction (tensor pipe) and the unary Linears (HBM: N*Cin read + N*Cout written) are separate
     # classes; "kpconv" = whole KPConv operators (aggregate + contraction, one- and two-kernel forms together)
     work["kpconv_contraction"] = dict(bytes=gemm_b, flops=gemm_f)
     work["linear"] = dict(bytes=lin_b, flops=lin_f)
     work["kpconv"] = dict(bytes=agg_b + gemm_b, flops=agg_f + gemm_f)
     return work, N
+
+
+def summarise_classes(prof, work, K, root=ROOT):
+    """Per-class device time of the profiled pass -> the `kernels` and `roofline` objects of the JSON line.
+    prof: class name -> (ms over K steps, event scopes over K steps); work: algorithmic_work()'s per-class bytes / flops."""
+    peaks = {}
+    pk = os.path.join(root, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    kernels = {}
+    agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
+           "kpconv_fused": ["kpconv_fused"], "kpconv_contraction": ["gemm"], "linear": ["linear"], "norm_act": ["norm_act"],
+           "pool": ["pool"], "projection": ["projection"]}
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    for name, parts in agg.items():
+        ms = sum(prof[p][0] for p in parts if p in prof) / K
+        n = sum(prof[p][1] for p in parts if p in prof) // K
+        ent = {"ms_per_step": round(ms, 4), "scopes_per_step": int(n), "share": round(ms * K / tot_ms, 4)}
+        if name in work and ms > 0:
+            if work[name]["bytes"]:
+                ent["GB/s"] = round(work[name]["bytes"] / ms / 1e6, 2)
+            if work[name]["flops"]:
+                ent["TFLOP/s"] = round(work[name]["flops"] / ms / 1e9, 3)
+            if work[name].get("gathered_bytes"):
+                # SURVEY 8d: the aggregation stage is an L2 -> SM gather; its rate is reported next to the algorithmic-HBM figure
+                # (the L2 gather cap measured with tools/micro/gather_bench.cu is ~12.8 TB/s)
+                ent["gathered_GB/s"] = round(work[name]["gathered_bytes"] / ms / 1e6, 1)
+        kernels[name] = ent
+    # whole KPConv operators: the fused kernel covers aggregate + contraction of its layers, so the three classes are summed
+    kp_ms = sum(kernels[k]["ms_per_step"] for k in ("kpconv_aggregate", "kpconv_fused", "kpconv_contraction"))
+    kernels["kpconv"] = {"ms_per_step": round(kp_ms, 4), "share": round(kp_ms * K / tot_ms, 4),
+                         "note": "kpconv_aggregate + kpconv_fused + kpconv_contraction"}
+    if kp_ms > 0:
+        kernels["kpconv"].update({"GB/s": round(work["kpconv"]["bytes"] / kp_ms / 1e6, 2),
+                                  "TFLOP/s": round(work["kpconv"]["flops"] / kp_ms / 1e9, 3)})
+    single = [k for k in kernels if k != "kpconv"]
+    dom = max(single, key=lambda k: kernels[k]["ms_per_step"])
+    traffic = None
+    tr_path = os.path.join(root, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        tj = json.load(open(tr_path))
+        traffic = tj.get(dom)       # DRAM bytes of the class over ONE step (ncu, same command), like `achieved`'s numerator
+    roof_extra = {"per": "step (all launches of the class)", "algorithmic_bytes": work.get(dom, {}).get("bytes"),
+                  "algorithmic_flops": work.get(dom, {}).get("flops") or None}
+    if dom == "kpconv_contraction":
+        # useful flops; the bf16x3 scheme issues 3 MMAs per useful one, so the tensor pipe is 3x busier than `achieved` says
+        ach = kernels[dom].get("TFLOP/s", 0.0)
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "pipe_frac": 3.0 * ach / tf_peak, "traffic": traffic, "peak_source": peak_src + ", bf16 dense sustained"}
+    else:
+        ach = kernels[dom].get("GB/s", 0.0)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src}
+    roof.update(roof_extra)
+    if "gathered_GB/s" in kernels[dom]:
+        roof["gathered_GB/s"] = kernels[dom]["gathered_GB/s"]
+        roof["note"] = ("an L2 -> SM gather of neighbour rows followed by small mma.sync products: `achieved` counts only the algorithmic HBM "
+                        "bytes (SURVEY 8d), `gathered_GB/s` is the rate of the gathered bytes (measured L2 gather cap ~12800 GB/s)")
+    return kernels, roof
 
 
 def quick_measure(workload, P, K, W, rank, world, dev, flush, dist):
@@ -707,51 +775,7 @@ def main():
 
     line, guard = None, None
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        kernels = {}
-        agg = {"subsample": ["subsample"], "radius": ["radius_build", "radius_query"], "kpconv_aggregate": ["kpconv_aggregate"],
-               "kpconv_fused": ["kpconv_fused"], "kpconv_contraction": ["gemm"], "linear": ["linear"], "norm_act": ["norm_act"],
-               "pool": ["pool"], "projection": ["projection"]}
-        tot_ms = sum(v[0] for v in prof.values()) or 1.0
-        for name, parts in agg.items():
-            ms = sum(prof[p][0] for p in parts if p in prof) / K
-            n = sum(prof[p][1] for p in parts if p in prof) // K
-            ent = {"ms_per_step": round(ms, 4), "scopes_per_step": int(n), "share": round(ms * K / tot_ms, 4)}
-            if name in work and ms > 0:
-                ent["GB/s"] = round(work[name]["bytes"] / ms / 1e6, 2)
-                if work[name]["flops"]:
-                    ent["TFLOP/s"] = round(work[name]["flops"] / ms / 1e9, 3)
-            kernels[name] = ent
-        # whole KPConv operators: the fused kernel covers aggregate + contraction of its layers, so the three classes are summed
-        kp_ms = sum(kernels[k]["ms_per_step"] for k in ("kpconv_aggregate", "kpconv_fused", "kpconv_contraction"))
-        kernels["kpconv"] = {"ms_per_step": round(kp_ms, 4), "share": round(kp_ms * K / tot_ms, 4),
-                             "GB/s": round(work["kpconv"]["bytes"] / kp_ms / 1e6, 2), "TFLOP/s": round(work["kpconv"]["flops"] / kp_ms / 1e9, 3),
-                             "note": "kpconv_aggregate + kpconv_fused + kpconv_contraction"}
-        single = [k for k in kernels if k != "kpconv"]
-        dom = max(single, key=lambda k: kernels[k]["ms_per_step"])
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path):
-            tj = json.load(open(tr_path))
-            traffic = tj.get(dom)       # DRAM bytes of the class over ONE step (ncu, same command), like `achieved`'s numerator
-        roof_extra = {"per": "step (all launches of the class)", "algorithmic_bytes": work.get(dom, {}).get("bytes"),
-                      "algorithmic_flops": work.get(dom, {}).get("flops") or None}
-        if dom == "kpconv_contraction":
-            # useful flops; the bf16x3 scheme issues 3 MMAs per useful one, so the tensor pipe is 3x busier than `achieved` says
-            ach = kernels[dom].get("TFLOP/s", 0.0)
-            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "pipe_frac": 3.0 * ach / tf_peak, "traffic": traffic, "peak_source": peak_src + ", bf16 dense sustained"}
-        else:
-            ach = kernels[dom].get("GB/s", 0.0)
-            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src}
-        roof.update(roof_extra)
+        kernels, roof = summarise_classes(prof, work, K)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
