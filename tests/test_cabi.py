@@ -83,3 +83,27 @@ def test_features_and_classes_argument_checks():
         cpp_subsampling.subsample_batch(pts, [4], features=[["a", "b"]] * 4)
     with pytest.raises(RuntimeError, match="Error parsing method"):
         cpp_subsampling.subsample_batch(pts, [4], method="nonsense")
+
+
+def test_header_is_plain_c_and_a_c_caller_fails_loudly_without_a_gpu(tmp_path):
+    """include/pcrcg_b200.h compiles as C99 and as C++11; examples/c_abi_demo.c links against the library and, on a box without a
+    CUDA device, gets a non-zero status and a message from pcrcg_last_error() (no crash, no CPU fallback).  On a GPU box it runs."""
+    import subprocess
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    inc = os.path.join(ROOT, "include")
+    cpp = tmp_path / "h.cpp"
+    cpp.write_text('#include "pcrcg_b200.h"\n')
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-pedantic", "-Werror", "-I", inc, "-c", str(cpp), "-o", str(tmp_path / "h.o")])
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(g.LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                           "-L", libdir, "-lpcrcg_b200", f"-Wl,-rpath,{libdir}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "libpcrcg_b200 version 100" in r.stdout
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "voxels" in r.stdout
+    else:
+        assert r.returncode == 2 and "pcrcg_subsample_batch_host failed:" in r.stdout and "cudaMalloc" in r.stdout
