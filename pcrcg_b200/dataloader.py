@@ -125,9 +125,10 @@ def build_pyramid(points, lengths, config, neighborhood_limits, device=None, pai
 
 
 def collate_fn_descriptor(list_data, config, neighborhood_limits, device="cuda"):
-    """datasets/dataloader.py:203-400 for the keys the KPConv path consumes.  ``list_data`` items
-    are dicts with ``src_pcd``, ``tgt_pcd`` ([N,3]) and ``src_feats``, ``tgt_feats`` ([N,C]); unlike the
-    reference any number of pairs may be stacked."""
+    """datasets/dataloader.py:203-400.  ``list_data`` items are dicts with ``src_pcd``, ``tgt_pcd`` ([N,3]) and ``src_feats``,
+    ``tgt_feats`` ([N,C]); unlike the reference any number of pairs may be stacked.  The pyramid keys (``points, neighbors, pools,
+    upsamples, stack_lengths, features``) are device tensors; for a single pair (the reference's only case, :207) the dict also
+    carries the reference's other keys, see :func:`_reference_extras`."""
     pts, lens, feats = [], [], []
     for d in list_data:
         for k in ("src", "tgt"):
@@ -137,7 +138,40 @@ def collate_fn_descriptor(list_data, config, neighborhood_limits, device="cuda")
             feats.append(np.asarray(d[f"{k}_feats"], dtype=np.float32))
     batch = build_pyramid(np.concatenate(pts), np.array(lens, np.int32), config, neighborhood_limits, device=device)
     batch["features"] = _dev_f32(np.concatenate(feats), batch["points"][0].device)
+    if len(list_data) == 1:
+        _reference_extras(batch, list_data[0], pts[0], pts[1])
     return batch
+
+
+# keys the reference's collate copies from the dataset item unchanged (datasets/dataloader.py:380-397)
+_IMAGE_KEYS = ("src1_inds2d", "src2_inds2d", "src3_inds2d", "tgt1_inds2d", "tgt2_inds2d", "tgt3_inds2d", "src1_inds3d", "src2_inds3d",
+               "src3_inds3d", "tgt1_inds3d", "tgt2_inds3d", "tgt3_inds3d", "src_color1", "src_color2", "src_color3", "tgt_color1",
+               "tgt_color2", "tgt_color3", "id_name", "detect_1", "detect_2", "detect_3", "detect_4", "des1", "des2", "des3", "des4",
+               "src_valid_map1", "src_valid_map2", "tgt_valid_map1", "tgt_valid_map2")
+
+
+def _reference_extras(batch, item, src, tgt):
+    """The remaining keys of the reference's dict for ONE pair (datasets/dataloader.py:359-397), as far as the dataset item carries
+    their inputs: rot / trans / correspondences / sample and the image keys are handed through, the raw clouds are returned as
+    float tensors, and the node labels of the coarsest level (``node_overlap_gt``, ``points2node``, :309-322) are computed on the
+    device from the ground-truth correspondences."""
+    for k in ("rot", "trans"):
+        if k in item:
+            batch[k] = torch.as_tensor(np.asarray(item[k]))
+    batch["src_pcd_raw"] = torch.from_numpy(np.ascontiguousarray(src)).float()
+    batch["tgt_pcd_raw"] = torch.from_numpy(np.ascontiguousarray(tgt)).float()
+    if "sample" in item:
+        batch["sample"] = item["sample"]
+    if "correspondences" in item:
+        batch["correspondences"] = item["correspondences"]
+        nodes = batch["points"][-1]
+        n_src = int(batch["stack_lengths"][-1][0].item())
+        sv, tv, s2n, t2n = point2node_correspondences(nodes[:n_src], src, nodes[n_src:], tgt, item["correspondences"])
+        batch["node_overlap_gt"] = torch.cat((sv, tv))
+        batch["points2node"] = torch.cat((s2n, t2n))
+    for key in item:
+        if key in _IMAGE_KEYS:
+            batch[key] = item[key]
 
 
 @torch.no_grad()

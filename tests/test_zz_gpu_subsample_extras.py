@@ -93,3 +93,33 @@ def test_more_than_64_distinct_labels_in_a_voxel_is_reported():
         cpp_subsampling.subsample_batch(pts, [65], classes=np.arange(65, dtype=np.int32), sampleDl=1.0)
     with pytest.raises(RuntimeError, match="more than 64 distinct labels"):
         ops.subsample_batch_ex(_t(pts), _t(np.array([65], np.int32)), 1.0, classes=_t(np.arange(65, dtype=np.int32)))
+
+
+def test_collate_returns_the_reference_dict_for_one_pair():
+    """collate_fn_descriptor (datasets/dataloader.py:203-400) for a single pair: the pyramid keys plus everything else the
+    reference's dict holds -- pass-through keys untouched, node labels of the coarsest level equal to the direct call"""
+    from pcrcg_b200 import blocks, pipeline, synthetic
+    src, tgt, _ = synthetic.match3d_pair(3, n_target=3000)
+    rng = np.random.default_rng(3)
+    corr = torch.from_numpy(np.stack([rng.integers(0, len(src), 700), rng.integers(0, len(tgt), 700)], 1))
+    vm = object()
+    item = dict(src_pcd=src, tgt_pcd=tgt, src_feats=np.ones((len(src), 1), np.float32), tgt_feats=np.ones((len(tgt), 1), np.float32),
+                rot=np.eye(3), trans=np.zeros((3, 1)), correspondences=corr, sample="7-scenes-redkitchen@0", src_valid_map1=vm,
+                not_a_reference_key=1)
+    cfg, limits = blocks.indoor_config(), pipeline.CALIBRATED_LIMITS["3dmatch_synthetic"]
+    b = dataloader.collate_fn_descriptor([item], cfg, limits, device=DEV)
+    want = {"points", "neighbors", "pools", "upsamples", "features", "stack_lengths", "rot", "trans", "correspondences", "src_pcd_raw",
+            "tgt_pcd_raw", "sample", "node_overlap_gt", "points2node", "src_valid_map1"}
+    assert want <= set(b) and "not_a_reference_key" not in b
+    assert b["correspondences"] is corr and b["src_valid_map1"] is vm and b["sample"] == "7-scenes-redkitchen@0"
+    assert torch.equal(b["rot"], torch.eye(3, dtype=torch.float64)) and tuple(b["trans"].shape) == (3, 1)
+    assert np.array_equal(b["src_pcd_raw"].numpy(), src.astype(np.float32)) and b["tgt_pcd_raw"].dtype == torch.float32
+    assert len(b["points"]) == 4 and b["features"].shape == (len(src) + len(tgt), 1)
+    nodes, n_src = b["points"][-1], int(b["stack_lengths"][-1][0])
+    sv, tv, s2n, t2n = dataloader.point2node_correspondences(nodes[:n_src], src, nodes[n_src:], tgt, corr)
+    assert torch.equal(b["node_overlap_gt"], torch.cat((sv, tv))) and torch.equal(b["points2node"], torch.cat((s2n, t2n)))
+    assert b["node_overlap_gt"].shape[0] == nodes.shape[0] and b["points2node"].shape[0] == len(src) + len(tgt)
+    assert float(b["node_overlap_gt"].min()) >= 0.0 and float(b["node_overlap_gt"].max()) <= 1.0
+    # several pairs stacked (not a reference case): only the pyramid keys
+    b2 = dataloader.collate_fn_descriptor([item, item], cfg, limits, device=DEV)
+    assert "rot" not in b2 and b2["stack_lengths"][0].numel() == 4
