@@ -28,18 +28,33 @@ def _dev_i32(t, device):
     return t.to(device=device, dtype=torch.int32, non_blocking=True)
 
 
+def _device_of(*ts):
+    """the CUDA device of the first device tensor among the arguments, else the current CUDA device: the reference hands these
+    functions CPU tensors / arrays (datasets/dataloader.py:273-301); here they are copied to the GPU, where all the work happens"""
+    for t in ts:
+        if torch.is_tensor(t) and t.is_cuda:
+            return t.device
+    return torch.device("cuda")
+
+
 def batch_grid_subsampling_kpconv(points, batches_len, features=None, labels=None, sampleDl=0.1, max_p=0, verbose=0,
                                   random_grid_orient=True):
     """-> (s_points [M,3] f32, s_len [B] i32[, s_features][, s_labels]) in the reference's order (datasets/dataloader.py:18-52),
     on the device of ``points`` (cuda)."""
+    dev = _device_of(points, batches_len)
+    points, batches_len = _dev_f32(points, dev), _dev_i32(batches_len, dev)
     if features is None and labels is None:
         return ops.subsample_batch(points, batches_len, sampleDl, max_p)
+    features = None if features is None else _dev_f32(features, dev)
+    labels = None if labels is None else _dev_i32(labels, dev)
     return ops.subsample_batch_ex(points, batches_len, sampleDl, max_p, features=features, classes=labels)
 
 
 def batch_neighbors_kpconv(queries, supports, q_batches, s_batches, radius, max_neighbors):
-    """-> int32 [Nq, min(max_neighbors, max_count)] (max_neighbors <= 0: full width)."""
-    return ops.batch_query(queries, supports, q_batches, s_batches, radius, max_neighbors)
+    """-> int32 [Nq, min(max_neighbors, max_count)] (max_neighbors <= 0: full width), on the device."""
+    dev = _device_of(queries, supports)
+    return ops.batch_query(_dev_f32(queries, dev), _dev_f32(supports, dev), _dev_i32(q_batches, dev), _dev_i32(s_batches, dev), radius,
+                           max_neighbors)
 
 
 @torch.no_grad()

@@ -123,3 +123,15 @@ def test_collate_returns_the_reference_dict_for_one_pair():
     # several pairs stacked (not a reference case): only the pyramid keys
     b2 = dataloader.collate_fn_descriptor([item, item], cfg, limits, device=DEV)
     assert "rot" not in b2 and b2["stack_lengths"][0].numel() == 4
+
+
+def test_dataloader_mirrors_accept_the_references_cpu_inputs(port):
+    """datasets/dataloader.py:273-301 hands batch_grid_subsampling_kpconv / batch_neighbors_kpconv CPU tensors; the mirrors copy
+    them to the GPU and return device tensors with the reference's values"""
+    pts, lens, _, _ = _case(11, 2, 3000, 1.0, 1, 1, 3)
+    sp, sl = dataloader.batch_grid_subsampling_kpconv(torch.from_numpy(pts), torch.from_numpy(lens), sampleDl=0.1)
+    op, ol = port.subsample_batch(pts, lens, 0.1)
+    assert sp.is_cuda and sl.is_cuda and np.array_equal(sp.cpu().numpy(), op) and np.array_equal(sl.cpu().numpy(), ol)
+    rows = dataloader.batch_neighbors_kpconv(op, pts, ol, lens.tolist(), 0.2, 30)           # NumPy arrays and a list
+    want = port.batch_query(op, pts, ol, lens, 0.2, limit=30)
+    assert rows.is_cuda and rows.dtype == torch.int32 and np.array_equal(rows.cpu().numpy(), want)
