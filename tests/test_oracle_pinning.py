@@ -242,3 +242,30 @@ def test_matching_port_vs_reference_golden():
     assert np.array_equal(r, g["mutual_rows"]) and np.array_equal(c, g["mutual_cols"])
     wo, w = mp.inlier_ratios(g["src_pcd"], g["tgt_pcd"], g["src_feat"], g["tgt_feat"], g["rot"], g["trans"])
     assert abs(wo - float(g["inlier_ratio_wo"])) < 1e-6 and abs(w - float(g["inlier_ratio_w"])) < 1e-6
+
+
+def test_cpu_pyramid_equals_the_references_own_collate():
+    """oracle/checks.cpu_pyramid (the checker behind tests/test_gpu_benchsize.py and bench.py's parity_check) against
+    tests/golden/callsites_ref.npz = the output of the reference's collate_fn_descriptor SOURCE executed unchanged over the
+    unmodified reference core (tests/golden/make_golden_callsites.py)"""
+    from oracle import checks
+    g = np.load(os.path.join(G, "callsites_ref.npz"))
+    pyr = checks.cpu_pyramid(g["col_src"], g["col_tgt"], g["col_limits"].tolist(), 0.025, 2.5, 4)
+    for l in range(4):
+        assert np.array_equal(pyr["points"][l], g[f"col_points_{l}"])
+        assert np.array_equal(pyr["stack_lengths"][l], g[f"col_stack_lengths_{l}"])
+        for k in ("neighbors", "pools", "upsamples"):
+            assert np.array_equal(pyr[k][l].astype(np.int64), g[f"col_{k}_{l}"]), (k, l)
+    assert int(g["rows_canonicalised"]) > 0          # the golden does contain tied rows
+
+
+def test_port_equals_the_references_subsampling_call_site(port):
+    """datasets/dataloader.py:14-52 executed from the reference's source (all four branches + max_p) vs the C port"""
+    g = np.load(os.path.join(G, "callsites_ref.npz"))
+    pts, lens, f, c = g["sub_points"], g["sub_lens"], g["sub_features"], g["sub_labels"]
+    for tag, kw in (("plain", {}), ("feat", dict(features=f)), ("lab", dict(classes=c)), ("both", dict(features=f, classes=c))):
+        out = port.subsample_batch_ex(pts, lens, sampleDl=0.06, **kw)
+        for i, o in enumerate(out):
+            assert np.array_equal(o, g[f"sub_{tag}_{i}"]), (tag, i)
+    out = port.subsample_batch(pts, lens, 0.06, 300)
+    assert np.array_equal(out[0], g["sub_maxp_0"]) and np.array_equal(out[1], g["sub_maxp_1"])

@@ -135,3 +135,51 @@ def test_dataloader_mirrors_accept_the_references_cpu_inputs(port):
     rows = dataloader.batch_neighbors_kpconv(op, pts, ol, lens.tolist(), 0.2, 30)           # NumPy arrays and a list
     want = port.batch_query(op, pts, ol, lens, 0.2, limit=30)
     assert rows.is_cuda and rows.dtype == torch.int32 and np.array_equal(rows.cpu().numpy(), want)
+
+
+# ---- the reference's own call sites (datasets/dataloader.py), golden = their SOURCE executed over the reference core ------------
+import os                                                                                      # noqa: E402
+
+_G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "callsites_ref.npz"))
+
+
+def test_subsampling_call_site_vs_reference_source():
+    """batch_grid_subsampling_kpconv (datasets/dataloader.py:14-52): every branch, CPU tensors in as the collate passes them"""
+    P, B = torch.from_numpy(_G["sub_points"]), torch.from_numpy(_G["sub_lens"])
+    f, c = torch.from_numpy(_G["sub_features"]), torch.from_numpy(_G["sub_labels"])
+    for tag, kw in (("plain", {}), ("feat", dict(features=f)), ("lab", dict(labels=c)), ("both", dict(features=f, labels=c))):
+        out = dataloader.batch_grid_subsampling_kpconv(P, B, sampleDl=0.06, **kw)
+        assert len(out) == 2 + len(kw)
+        for i, o in enumerate(out):
+            assert np.array_equal(o.cpu().numpy(), _G[f"sub_{tag}_{i}"]), (tag, i)
+    out = dataloader.batch_grid_subsampling_kpconv(P, B, sampleDl=0.06, max_p=300)
+    assert np.array_equal(out[0].cpu().numpy(), _G["sub_maxp_0"]) and np.array_equal(out[1].cpu().numpy(), _G["sub_maxp_1"])
+
+
+def test_neighbour_call_site_vs_reference_source():
+    """batch_neighbors_kpconv (datasets/dataloader.py:54-69): truncated to max_neighbors, and full width for max_neighbors = 0"""
+    P, B = torch.from_numpy(_G["sub_points"]), torch.from_numpy(_G["sub_lens"])
+    sp, sl = torch.from_numpy(_G["sub_plain_0"]), torch.from_numpy(_G["sub_plain_1"])
+    rows = dataloader.batch_neighbors_kpconv(sp, P, sl, B, 0.15, 20)
+    assert np.array_equal(rows.cpu().numpy(), _G["nb_pool_20"])
+    rows = dataloader.batch_neighbors_kpconv(sp, sp, sl, sl, 0.15, 0)
+    assert np.array_equal(rows.cpu().numpy(), _G["nb_conv_full"])
+
+
+def test_collate_vs_reference_source():
+    """collate_fn_descriptor (datasets/dataloader.py:203-400) on one pair: every list of the pyramid, the features and the node
+    labels of the coarsest level against the reference's own function"""
+    from pcrcg_b200 import blocks
+    src, tgt, corr = _G["col_src"], _G["col_tgt"], torch.from_numpy(_G["col_corr"])
+    item = dict(src_pcd=src, tgt_pcd=tgt, src_feats=np.ones((len(src), 1), np.float32), tgt_feats=np.ones((len(tgt), 1), np.float32),
+                rot=np.eye(3, dtype=np.float32), trans=np.zeros((3, 1), np.float32), correspondences=corr, sample="synthetic@17")
+    b = dataloader.collate_fn_descriptor([item], blocks.indoor_config(), _G["col_limits"].tolist(), device=DEV)
+    assert set(_G["col_keys"].tolist()) <= set(b)
+    for l in range(4):
+        assert np.array_equal(b["points"][l].cpu().numpy(), _G[f"col_points_{l}"])
+        assert np.array_equal(b["stack_lengths"][l].cpu().numpy(), _G[f"col_stack_lengths_{l}"])
+        for k in ("neighbors", "pools", "upsamples"):
+            assert np.array_equal(b[k][l].cpu().numpy().astype(np.int64), _G[f"col_{k}_{l}"]), (k, l)
+    assert np.array_equal(b["features"].cpu().numpy(), _G["col_features"])
+    assert np.array_equal(b["points2node"].cpu().numpy(), _G["col_points2node"])
+    assert np.allclose(b["node_overlap_gt"].cpu().numpy(), _G["col_node_overlap_gt"], rtol=0, atol=1e-6)
