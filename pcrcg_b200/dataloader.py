@@ -190,13 +190,25 @@ def _reference_extras(batch, item, src, tgt):
 
 
 @torch.no_grad()
-def calibrate_neighbors(pair_iter, config, keep_ratio=0.8, samples_threshold=2000, device="cuda"):
-    """datasets/dataloader.py:402-434: histogram of neighbourhood sizes per layer over the pairs of
-    ``pair_iter`` (items: (src [N,3], tgt [M,3])), limit = number of histogram bins whose cumulated
-    mass stays below keep_ratio."""
+def _calibration_pairs(dataset):
+    """the reference walks ``dataset[i] for i in range(len(dataset))`` (datasets/dataloader.py:411-413); any iterable works here.
+    Items: the dataset's dicts (``src_pcd`` / ``tgt_pcd``) or plain (src, tgt) tuples."""
+    if hasattr(dataset, "__len__") and hasattr(dataset, "__getitem__") and not isinstance(dataset, (list, tuple)):
+        items = (dataset[i] for i in range(len(dataset)))
+    else:
+        items = iter(dataset)
+    for it in items:
+        yield (it["src_pcd"], it["tgt_pcd"]) if isinstance(it, dict) else (it[0], it[1])
+
+
+def calibrate_neighbors(dataset, config, collate_fn=None, keep_ratio=0.8, samples_threshold=2000, device="cuda"):
+    """datasets/dataloader.py:402-434, same signature: histogram of neighbourhood sizes per layer over the pairs of ``dataset``,
+    limit = number of histogram bins whose cumulated mass stays below keep_ratio.  ``collate_fn`` is accepted for call
+    compatibility and not used: the un-truncated neighbour counts come straight from the search kernel instead of from
+    905-column index lists."""
     hist_n = int(np.ceil(4 / 3 * np.pi * (config.deform_radius + 1) ** 3))
     neighb_hists = np.zeros((config.num_layers, hist_n), dtype=np.int64)
-    for src, tgt in pair_iter:
+    for src, tgt in _calibration_pairs(dataset):
         pts = np.concatenate([src, tgt]).astype(np.float32)
         lens = np.array([len(src), len(tgt)], np.int32)
         b = build_pyramid(pts, lens, config, [hist_n] * 5, device=device, return_counts=True)
