@@ -233,3 +233,119 @@ def test_gated_ring_tail_tiles():
     for nt in (0, 1, 2, 3, 4):
         for seed in range(50):
             run(True, 3, seed, ntiles=nt)
+
+
+# ---- exhaustive exploration of a small configuration ------------------------------------------------------------------------------
+def explore(W, cif, ntiles, TILE, SLOTS, gate, limit=8_000_000):
+    """Every interleaving of a small configuration of the same protocol (W producer warps, TILE points per tile, the MMA thread,
+    the completion of its commits as a separate, arbitrarily delayed event, one epilogue actor): depth-first over all enabled
+    actions with a visited set.  -> ("safe", states) | ("violation: ...", detail) | ("deadlock", state) | ("limit", states)"""
+    ACCS = 2
+    m_end = ntiles * TILE
+    # state: (next_point, tiles_issued, mma_i, mma_stage, pending commits (tuple of tile ids), epi_i,
+    #         full (completed, pending) per slot, empty completed per slot, accfull completed per acc, accempty completed per acc,
+    #         rows per slot (tuple of (row,tile) sorted), consumed count (in-order commits => consumed = set of first k tiles),
+    #         producers: tuple of (queue tuple, stage))   stage: 0 = need claim (init or loop), 1 = at gate, 2 = at parity, 9 = done
+    def initial():
+        prods = tuple(((), 0) for _ in range(W))
+        full = tuple((0, TILE) for _ in range(SLOTS))
+        return (0, 0, 0, 0, (), 0, full, (0,) * SLOTS, (0,) * ACCS, (0,) * ACCS, tuple(() for _ in range(SLOTS)), 0, prods)
+
+    def test(completed, parity):
+        return (completed & 1) != parity
+
+    seen = set()
+    stack = [initial()]
+    n = 0
+    while stack:
+        s = stack.pop()
+        if s in seen:
+            continue
+        seen.add(s)
+        n += 1
+        if n > limit:
+            return "limit", n
+        (nextp, issued, mi, mstage, pend, ei, full, empty, accfull, accempty, rows, consumed, prods) = s
+        succ = []
+        # ---- producers
+        for w, (q, st) in enumerate(prods):
+            if st == 9:
+                continue
+            if st == 0:
+                if len(q) < cif - 1:                       # initial claims
+                    nq = q + (nextp,)
+                    np_ = prods[:w] + ((nq, 0),) + prods[w + 1:]
+                    succ.append((nextp + 1, issued, mi, mstage, pend, ei, full, empty, accfull, accempty, rows, consumed, np_))
+                elif q[0] >= m_end:
+                    np_ = prods[:w] + ((q, 9),) + prods[w + 1:]
+                    succ.append((nextp, issued, mi, mstage, pend, ei, full, empty, accfull, accempty, rows, consumed, np_))
+                else:                                       # loop head: claim fm, compute m, arrive at the store
+                    nq = q + (nextp,)
+                    np_ = prods[:w] + ((nq, 1 if gate else 2),) + prods[w + 1:]
+                    succ.append((nextp + 1, issued, mi, mstage, pend, ei, full, empty, accfull, accempty, rows, consumed, np_))
+            elif st == 1:
+                i = q[0] // TILE
+                if issued >= i - (SLOTS - 1):
+                    np_ = prods[:w] + ((q, 2),) + prods[w + 1:]
+                    succ.append((nextp, issued, mi, mstage, pend, ei, full, empty, accfull, accempty, rows, consumed, np_))
+            elif st == 2:
+                m = q[0]
+                i, row = divmod(m, TILE)
+                slot, use = i % SLOTS, i // SLOTS
+                if test(empty[slot], (use & 1) ^ 1):
+                    if i >= SLOTS and consumed <= i - SLOTS:
+                        return "violation: overwrite", (w, m, i, empty[slot], use)
+                    nrows = rows[:slot] + (tuple(sorted(rows[slot] + ((row, i),))),) + rows[slot + 1:]
+                    c, p = full[slot]
+                    p -= 1
+                    if p == 0:
+                        c, p = c + 1, TILE
+                    nfull = full[:slot] + ((c, p),) + full[slot + 1:]
+                    np_ = prods[:w] + ((q[1:], 0),) + prods[w + 1:]
+                    succ.append((nextp, issued, mi, mstage, pend, ei, nfull, empty, accfull, accempty, nrows, consumed, np_))
+        # ---- MMA thread
+        if mi < ntiles:
+            slot, acc = mi % SLOTS, mi % ACCS
+            if mstage == 0:
+                if test(accempty[acc], ((mi // ACCS) & 1) ^ 1):
+                    succ.append((nextp, issued, mi, 1, pend, ei, full, empty, accfull, accempty, rows, consumed, prods))
+            else:
+                if test(full[slot][0], (mi // SLOTS) & 1):
+                    if rows[slot] != tuple((r, mi) for r in range(TILE)):
+                        return "violation: mma reads", (mi, rows[slot])
+                    succ.append((nextp, mi + 1, mi + 1, 0, pend + (mi,), ei, full, empty, accfull, accempty, rows, consumed, prods))
+        # ---- completion of the oldest pending commit
+        if pend:
+            t = pend[0]
+            slot, acc = t % SLOTS, t % ACCS
+            nrows = rows[:slot] + ((),) + rows[slot + 1:]
+            nempty = empty[:slot] + (empty[slot] + 1,) + empty[slot + 1:]
+            naf = accfull[:acc] + (accfull[acc] + 1,) + accfull[acc + 1:]
+            succ.append((nextp, issued, mi, mstage, pend[1:], ei, full, nempty, naf, accempty, nrows, consumed + 1, prods))
+        # ---- epilogue
+        if ei < ntiles:
+            acc = ei % ACCS
+            if test(accfull[acc], (ei // ACCS) & 1):
+                nae = accempty[:acc] + (accempty[acc] + 1,) + accempty[acc + 1:]
+                succ.append((nextp, issued, mi, mstage, pend, ei + 1, full, empty, accfull, nae, rows, consumed, prods))
+        if not succ:
+            done = all(st == 9 for _, st in prods) and mi == ntiles and ei == ntiles and not pend
+            if not done:
+                return "deadlock", s
+        stack.extend(succ)
+    return "safe", n
+
+
+def test_ungated_ring_has_a_violating_schedule_in_the_smallest_configuration():
+    """3 warps, 3 claims in flight, one point per tile, 7 tiles: the warp holding claims (1, 2, 6) finishes tiles 1 and 2 while tile 0
+    is still being computed and passes the parity wait of slot 0 for tile 6 on a barrier that has not completed once"""
+    kind, detail = explore(3, 3, 7, 1, SLOTS, gate=False)
+    assert kind == "violation: overwrite", (kind, detail)
+    assert explore(3, 3, 6, 1, SLOTS, gate=False)[0] == "safe"          # no third use of a slot: nothing to confuse
+
+
+def test_gated_ring_is_safe_under_every_interleaving_of_the_smallest_configuration():
+    """the same configuration with the gate: the complete reachable state space (~2.4 M states) holds no overwrite, no mixed tile
+    under the MMAs and no deadlock"""
+    kind, states = explore(3, 3, 7, 1, SLOTS, gate=True)
+    assert kind == "safe" and states > 1_000_000, (kind, states)
