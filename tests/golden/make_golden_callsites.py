@@ -6,7 +6,7 @@ behind a restatement of the CPython glue's tuple conventions (wrapper.cpp:318-32
 rows are put into the canonical (d2, index) tie order before the reference's own code truncates them.
 
 Needs /root/reference; never runs on the GPU box.  Re-run:  python tests/golden/make_golden_callsites.py
--> tests/golden/callsites_ref.npz (inputs + the reference's outputs), checked on the GPU by tests/test_zz_gpu_subsample_extras.py.
+-> tests/golden/callsites_ref.npz (inputs + the reference's outputs), checked on the GPU by tests/test_zz_gpu_round2_late.py.
 """
 import ast
 import os

@@ -101,30 +101,6 @@ def test_fused_strided_geometry_and_wide_lists(limit):
     assert fused.shape == ref.shape and _err(fused, ref) < 1e-4
 
 
-def test_fused_tile_ring_under_ragged_neighbourhoods():
-    """Regression test of the tile-ring race (tests/test_fused_protocol.py): neighbourhoods cut to random lengths mix
-    1-k-step and 4-k-step points, so the 13 producer warps of a CTA drift apart over ~100 tiles each; the kernel must give the
-    two-kernel path's result, and the same bits on every repetition."""
-    q, s, rows, seg = _geometry(21, 20000, 64, n_pairs=3)
-    ns, width = s.shape[0], rows.shape[1]
-    g = torch.Generator().manual_seed(21)
-    keep = torch.randint(1, width + 1, (rows.shape[0], 1), generator=g).to(DEV)
-    keep[::5] = width                                                     # every fifth point keeps its full list
-    cols = torch.arange(width, device=DEV).view(1, -1)
-    rows = torch.where(cols < keep, rows, torch.full_like(rows, ns)).contiguous()
-    x = torch.randn(ns, 64, generator=g)
-    w = torch.randn(15, 64, 64, generator=g) / np.sqrt(15 * 64)
-    kp = torch.randn(15, 3, generator=g) * 0.03
-    xp = _planes(x.to(DEV))
-    two, _, _ = _run(0, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
-    first, _, _ = _run(1, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
-    assert _err(first, two) < 1e-4, _err(first, two)
-    first = first.clone()
-    for _ in range(15):
-        again, _, _ = _run(1, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
-        assert torch.equal(again, first)
-
-
 def test_fused_tiny_and_empty_neighbourhoods():
     """fewer points than one 8-point tile; queries whose lists hold shadows only give exact zeros"""
     g = torch.Generator().manual_seed(5)

@@ -3,7 +3,7 @@ the code nvcc compiles into k_bary_feat / k_label_vote / k_gather_extra -- compi
 geometry, against the CPU oracle.  The workspace arrays the kernels read (sorted voxel runs, first-occurrence ranks, the final
 lists k_order leaves in seqA / seqB) are rebuilt here with NumPy from the oracle's voxel keys and output order, with voxel slots in
 a random order as the GPU's hash table produces them.  What this does NOT cover: the plain pipeline that produces those arrays on
-the GPU (bit-exact in tests/test_gpu_preprocess.py) and the launch plumbing (tests/test_zz_gpu_subsample_extras.py)."""
+the GPU (bit-exact in tests/test_gpu_preprocess.py) and the launch plumbing (tests/test_zz_gpu_round2_late.py)."""
 import ctypes as C
 import os
 import subprocess

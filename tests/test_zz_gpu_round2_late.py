@@ -1,14 +1,19 @@
-"""GPU parity: subsample_batch(features=, classes=) -- grid_subsampling.cpp:34-102, wrapper.cpp:103-326 -- through the host C-ABI
-entry (the reference's module mirror) and the device entry, bit for bit against the CPU oracle (oracle/port.c, pinned to the
-unmodified reference core by tests/test_label_vote_host.py).
+"""GPU tests written AFTER round 2's GPU budget was spent: none of them had run on a B200 when they were committed, so the file
+sorts last on purpose (pytest -x reaches it after everything that has been green on the GPU).
 
-Written after this round's GPU budget was spent: the CUDA kernels behind it (k_bary_feat, k_label_vote, k_gather_extra) have
-not run on a B200 yet; the per-voxel vote routine itself is pinned on the CPU.  The file sorts last on purpose."""
+* subsample_batch(features=, classes=) -- grid_subsampling.cpp:34-102, wrapper.cpp:103-326 -- through the host C-ABI entry (the
+  reference's module mirror) and the device entry, bit for bit against the CPU oracle (oracle/port.c, pinned to the unmodified
+  reference core by tests/test_label_vote_host.py; the kernels' thread bodies are run on the CPU by
+  tests/test_subsample_extras_host.py)
+* collate_fn_descriptor / batch_grid_subsampling_kpconv / batch_neighbors_kpconv against the golden made by executing the reference's
+  own source (tests/golden/make_golden_callsites.py)
+* regression test of the fused KPConv's tile ring under ragged neighbourhoods"""
 import numpy as np
 import pytest
 import torch
 
 import oracle
+import test_gpu_kpconv_fused as kf
 from pcrcg_b200 import dataloader, ops
 from pcrcg_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as cpp_subsampling
 
@@ -183,3 +188,36 @@ def test_collate_vs_reference_source():
     assert np.array_equal(b["features"].cpu().numpy(), _G["col_features"])
     assert np.array_equal(b["points2node"].cpu().numpy(), _G["col_points2node"])
     assert np.allclose(b["node_overlap_gt"].cpu().numpy(), _G["col_node_overlap_gt"], rtol=0, atol=1e-6)
+
+
+# ---- fused KPConv: tile ring ----------------------------------------------------------------------------------------------------
+def test_fused_tile_ring_under_ragged_neighbourhoods():
+    """Regression test of the tile-ring race (tests/test_fused_protocol.py): neighbourhoods cut to random lengths mix
+    1-k-step and 4-k-step points, so the 13 producer warps of a CTA drift apart over ~100 tiles each; the kernel must give the
+    two-kernel path's result, and the same bits on every repetition."""
+    q, s, rows, seg = kf._geometry(21, 20000, 64, n_pairs=3)
+    ns, width = s.shape[0], rows.shape[1]
+    g = torch.Generator().manual_seed(21)
+    keep = torch.randint(1, width + 1, (rows.shape[0], 1), generator=g).to(DEV)
+    keep[::5] = width                                                     # every fifth point keeps its full list
+    cols = torch.arange(width, device=DEV).view(1, -1)
+    rows = torch.where(cols < keep, rows, torch.full_like(rows, ns)).contiguous()
+    x = torch.randn(ns, 64, generator=g)
+    w = torch.randn(15, 64, 64, generator=g) / np.sqrt(15 * 64)
+    kp = torch.randn(15, 3, generator=g) * 0.03
+    xp = kf._planes(x.to(DEV))
+    from pcrcg_b200._lib import lib, check
+    try:
+        _ring_body(q, s, rows, xp, kp, w, seg)
+    finally:
+        check(lib().pcrcg_set_option(b"kpconv_fused", 1))
+
+
+def _ring_body(q, s, rows, xp, kp, w, seg):
+    two, _, _ = kf._run(0, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
+    first, _, _ = kf._run(1, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
+    assert kf._err(first, two) < 1e-4, kf._err(first, two)
+    first = first.clone()
+    for _ in range(15):
+        again, _, _ = kf._run(1, q, s, rows, xp, kp.to(DEV), w.to(DEV), seg)
+        assert torch.equal(again, first)
