@@ -349,3 +349,21 @@ def test_gated_ring_is_safe_under_every_interleaving_of_the_smallest_configurati
     under the MMAs and no deadlock"""
     kind, states = explore(3, 3, 7, 1, SLOTS, gate=True)
     assert kind == "safe" and states > 1_000_000, (kind, states)
+
+
+def test_model_constants_are_the_kernels():
+    """the model's ring geometry and the gate it assumes are what csrc/kpconv_fused.cu compiles"""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pcrcg_b200", "csrc", "kpconv_fused.cu")).read()
+    const = {k: int(v) for k, v in re.findall(r"constexpr int (FZ_\w+) = (\d+);", src)}
+    assert const["FZ_SLOTS"] == SLOTS and const["FZ_TILE"] == TILE and const["FZ_PW"] == 13
+    assert "mbar_init(full_bar(s), FZ_TILE)" in src and "mbar_init(empty_bar(s), 1)" in src and "mbar_init(accempty_bar(a), 4)" in src
+    # the gate: producers read the issued-tile counter before the parity wait, the MMA thread publishes it after its commits
+    gate = src.index("lds_acquire(tiles_issued) < i - (FZ_SLOTS - 1)")
+    wait = src.index("mbar_wait(empty_bar(slot), (uint32_t)(((i / FZ_SLOTS) & 1) ^ 1))")
+    assert gate < wait
+    assert src.index("umma_commit(empty_bar(slot));") < src.index("sts_release(tiles_issued, i + 1);")
+    # three claims per warp in flight: two before the loop, one per iteration
+    body = src[src.index("int m = claim();"):src.index("store_point(m, 1.0f")]
+    assert body.count("claim()") == 3
