@@ -92,6 +92,32 @@ def test_all_points_in_one_voxel_many_tied_labels(port):
         _same(want, cpp_subsampling.subsample_batch(pts, [D], classes=c, sampleDl=1.0))
 
 
+def test_voxel_counts_around_the_rehash_schedule(port):
+    """clouds with 1 ... 300 voxels: k_order leaves the final list in seqA or seqB depending on the number of rehash epochs
+    (13 / 29 / 59 / 127 / 257 buckets); the gather of features and classes must follow it"""
+    rng = np.random.default_rng(99)
+    for M in (1, 2, 12, 13, 14, 28, 29, 30, 59, 60, 127, 128, 257, 258, 300):
+        g = int(np.ceil(M ** (1 / 3))) + 1
+        cells = rng.permutation(g ** 3)[:M]
+        centres = np.stack([cells % g, (cells // g) % g, cells // (g * g)], 1).astype(np.float32) + 0.5
+        pts = np.repeat(centres, 3, axis=0) + rng.uniform(-0.3, 0.3, size=(3 * M, 3)).astype(np.float32)
+        pts = pts[rng.permutation(len(pts))].astype(np.float32)
+        lens = np.array([len(pts)], np.int32)
+        f = rng.standard_normal((len(pts), 2)).astype(np.float32)
+        c = rng.integers(0, 3, size=(len(pts), 1)).astype(np.int32)
+        want = port.subsample_batch_ex(pts, lens, features=f, classes=c, sampleDl=1.0)
+        assert len(want[0]) == M
+        _same(want, cpp_subsampling.subsample_batch(pts, lens, features=f, classes=c, sampleDl=1.0))
+    # and two clouds of different parity in one batch
+    a = (rng.random((40, 3)) * 3).astype(np.float32)
+    b = (rng.random((400, 3)) * 6).astype(np.float32)
+    pts, lens = np.concatenate([a, b]), np.array([40, 400], np.int32)
+    f = rng.standard_normal((440, 3)).astype(np.float32)
+    c = rng.integers(0, 4, size=(440, 1)).astype(np.int32)
+    _same(port.subsample_batch_ex(pts, lens, features=f, classes=c, sampleDl=1.0),
+          cpp_subsampling.subsample_batch(pts, lens, features=f, classes=c, sampleDl=1.0))
+
+
 def test_more_than_64_distinct_labels_in_a_voxel_is_reported():
     pts = np.zeros((65, 3), np.float32)
     with pytest.raises(RuntimeError, match="more than 64 distinct labels"):
