@@ -107,3 +107,21 @@ def test_header_is_plain_c_and_a_c_caller_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 0 and "voxels" in r.stdout
     else:
         assert r.returncode == 2 and "pcrcg_subsample_batch_host failed:" in r.stdout and "cudaMalloc" in r.stdout
+
+
+def test_host_entry_points_marshal_and_fail_loudly_without_a_gpu():
+    """On a box without a CUDA device the host-buffer entry points are still CALLED (every argument marshalled through the binding
+    table: a wrong count or type would raise ctypes.ArgumentError) and answer with the library's error, not with a result."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU tests")
+    from pcrcg_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as cpp_subsampling
+    from pcrcg_b200.cpp_wrappers.cpp_neighbors import radius_neighbors as cpp_neighbors
+    pts = np.random.default_rng(0).random((50, 3)).astype(np.float32)
+    for kw in ({}, dict(features=np.ones((50, 2), np.float32)), dict(classes=np.zeros(50, np.int32)),
+               dict(features=np.ones((50, 2), np.float32), classes=np.zeros((50, 3), np.int32))):
+        with pytest.raises(RuntimeError, match="cudaMalloc|CUDA|cuda"):
+            cpp_subsampling.subsample_batch(pts, [50], sampleDl=0.1, **kw)
+    with pytest.raises(RuntimeError, match="cudaMalloc|CUDA|cuda"):
+        cpp_neighbors.batch_query(pts, pts, [50], [50], radius=0.2)
