@@ -125,3 +125,16 @@ def test_host_entry_points_marshal_and_fail_loudly_without_a_gpu():
             cpp_subsampling.subsample_batch(pts, [50], sampleDl=0.1, **kw)
     with pytest.raises(RuntimeError, match="cudaMalloc|CUDA|cuda"):
         cpp_neighbors.batch_query(pts, pts, [50], [50], radius=0.2)
+
+
+def test_subsample_ex_device_entry_marshals_and_checks_its_arguments():
+    from pcrcg_b200 import _lib
+    L = _lib.lib()
+    base, ex = L.pcrcg_subsample_ws_bytes(1000, 2), L.pcrcg_subsample_ex_ws_bytes(1000, 2, 4, 1)
+    assert ex >= base + 1000 * 4 * 4 + 1000 * 4 and L.pcrcg_subsample_ex_ws_bytes(1000, 2, 0, 0) >= base
+    rc = L.pcrcg_subsample_batch_ex_dev(None, 10, None, 1, 0.1, 0, None, 0, None, 0, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and b"workspace too small" in L.pcrcg_last_error()
+    rc = L.pcrcg_subsample_batch_ex_dev(None, 10, None, 2, 0.1, 0, None, 0, 1, 2, None, None, None, 1, 1, None, 0, None)
+    assert rc != 0 and b"single cloud only" in L.pcrcg_last_error()      # classes with 2 columns and 2 clouds
+    rc = L.pcrcg_subsample_batch_ex_dev(None, 10, None, 1, 0.1, 0, 1, 3, None, 0, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and b"features need" in L.pcrcg_last_error()          # features without an output buffer
