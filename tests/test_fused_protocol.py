@@ -332,7 +332,8 @@ def explore(W, cif, ntiles, TILE, SLOTS, gate, limit=8_000_000):
             done = all(st == 9 for _, st in prods) and mi == ntiles and ei == ntiles and not pend
             if not done:
                 return "deadlock", s
-        stack.extend(succ)
+        # the producer warps are interchangeable: states that differ only by a permutation of them are one state
+        stack.extend(t[:12] + (tuple(sorted(t[12])),) for t in succ)
     return "safe", n
 
 
@@ -345,10 +346,10 @@ def test_ungated_ring_has_a_violating_schedule_in_the_smallest_configuration():
 
 
 def test_gated_ring_is_safe_under_every_interleaving_of_the_smallest_configuration():
-    """the same configuration with the gate: the complete reachable state space (~2.4 M states) holds no overwrite, no mixed tile
-    under the MMAs and no deadlock"""
+    """the same configuration with the gate: the complete reachable state space (2.36 M states, ~0.4 M up to the permutation of the
+    warps) holds no overwrite, no mixed tile under the MMAs and no deadlock"""
     kind, states = explore(3, 3, 7, 1, SLOTS, gate=True)
-    assert kind == "safe" and states > 1_000_000, (kind, states)
+    assert kind == "safe" and states > 300_000, (kind, states)
 
 
 def test_model_constants_are_the_kernels():
