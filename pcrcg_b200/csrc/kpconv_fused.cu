@@ -21,7 +21,9 @@
 //               query point per warp at a time; the finished [16 kp x 64 ch] fragments are scaled by 1/neighbour count
 //               (models/blocks.py:369-372), split hi/lo and stored as row (point % 8) of the tile's 15 x 2 swizzle-128B
 //               K-major atoms -- the canonical UMMA operand layout, conflict-free 16-byte stores -- then
-//               fence.proxy.async + mbarrier arrive (8 arrivals complete a tile)
+//               fence.proxy.async + mbarrier arrive (8 arrivals complete a tile); before a warp tests a slot's "empty" barrier for
+//               tile i it waits until tile i - 3 has been issued (tiles_issued, see below): phase-parity waits are only
+//               unambiguous one completion ahead
 //   warp 4      MMA issuer: per tile 15 x 4 tcgen05.mma.kind::f16 (A from TMEM, B from the tile), tcgen05.commit frees the
 //               tile slot and publishes the accumulator
 //   warps 0-3   epilogue: tcgen05.ld of the 16 accumulator columns (thread = output channel), hi + lo columns, W_lo rows
